@@ -1,0 +1,564 @@
+// sf_api.cu — C ABI (include/staticfusion_b200.h) and host-side schedule of the B200 StaticFusion solver.
+//
+// The host enqueues a static schedule (runSolver's loop nest, FrontEnd.cpp:1094-1132, unrolled to its
+// maximum trip counts); all data-dependent exits are per-pair device flags, so one batch is solved
+// without any host synchronisation.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sf_kernels.cuh"
+
+using namespace sf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return fail(SF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct sf_ctx {
+    sf_params p;
+    DevParams dp;
+    int device = 0, max_batch = 0, flags = 0;
+    int levels = 0;
+    LevelGeom geom[MAX_LEVELS];
+    cudaStream_t stream = nullptr;
+    Arena a{};
+    int* d_cur_idx = nullptr;
+    int* d_pred_idx = nullptr;
+    float* d_twist_in = nullptr;
+    int n_frames_cap = 0;
+    // current batch
+    int n_pairs = 0, n_frames = 0;
+    bool uploaded = false, solved = false;
+    int stop_step = -1;
+    int launches = 0;
+    // drop-in trio state
+    std::vector<float> h_cur_d, h_cur_i, h_pred_d, h_pred_i;
+    bool have_cur = false, have_pred = false, trio_pyr_pred = false;
+    float h_twist_old[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<PairOut> h_out;
+};
+
+static void fill_dev_params(sf_ctx* c) {
+    const sf_params& p = c->p;
+    DevParams& d = c->dp;
+    d.ctf_levels = p.ctf_levels; d.max_iter_per_level = p.max_iter_per_level; d.max_iter_irls = p.max_iter_irls;
+    d.use_motion_filter = p.use_motion_filter; d.enable_segmentation = p.enable_segmentation;
+    d.k_photometric_res = p.k_photometric_res; d.irls_delta_threshold = p.irls_delta_threshold;
+    d.kc_cauchy = p.kc_cauchy; d.kb = p.kb; d.kz = p.kz; d.lambda_reg = p.lambda_reg; d.lambda_prior = p.lambda_prior;
+    d.previous_speed_const_weight = p.previous_speed_const_weight; d.previous_speed_eig_weight = p.previous_speed_eig_weight;
+    d.outer_exit_threshold = p.outer_exit_threshold;
+    for (int i = 0; i < MAX_LEVELS; i++) d.exp_neg_level[i] = expf(-(float)i);  // FrontEnd.cpp:745
+    // k-means seeds, KMeans.cpp:76-84 (evaluated at half resolution)
+    const int rows_km = p.rows / 2, cols_km = p.cols / 2;
+    const unsigned vert_div = (unsigned)std::ceil(std::sqrt((double)NC));
+    const float u_div = float(cols_km) / float(NC + 1);
+    const float v_div = float(rows_km) / float(vert_div + 1);
+    for (unsigned i = 0; i < (unsigned)NC; i++) {
+        d.km_u_label[i] = (float)(unsigned)std::round((i + 1) * u_div);
+        d.km_v_label[i] = (float)(unsigned)std::round((i % vert_div + 1) * v_div);
+    }
+    const float t = 0.03f * 120.f / float(p.rows);  // KMeans.cpp:300
+    d.conn_dist2_threshold = t * t;
+}
+
+static int validate(const sf_params* p, int max_batch) {
+    if (!p) return fail(SF_E_INVALID, "params is NULL");
+    if (p->rows <= 0 || p->cols <= 0) return fail(SF_E_INVALID, "rows/cols must be positive");
+    if (p->ctf_levels < 1 || p->ctf_levels > MAX_LEVELS) return fail(SF_E_INVALID, "ctf_levels must be in [1,8]");
+    if (p->enable_segmentation && p->ctf_levels < 2) return fail(SF_E_INVALID, "segmentation needs ctf_levels >= 2 (k-means runs at level 1)");
+    if (p->max_iter_per_level < 1 || p->max_iter_irls < 1) return fail(SF_E_INVALID, "iteration counts must be >= 1");
+    if (max_batch < 1) return fail(SF_E_INVALID, "max_batch must be >= 1");
+    for (int l = 0; l < p->ctf_levels; l++) {
+        const int r = p->rows >> l, c = p->cols >> l;
+        if (r < 3 || c < 4 || (c % 4) != 0) return fail(SF_E_INVALID, "every pyramid level needs cols % 4 == 0 and rows >= 3");
+        if (((p->rows >> l) << l) != p->rows || ((p->cols >> l) << l) != p->cols)
+            return fail(SF_E_INVALID, "rows and cols must be divisible by 2^(ctf_levels-1)");
+    }
+    if ((long long)(p->rows / 2) * (p->rows / 2) + (long long)(p->cols / 2) * (p->cols / 2) >= 1000000LL)
+        return fail(SF_E_INVALID, "resolution exceeds the reference's k-means seed range (KMeans.cpp:91)");
+    return SF_OK;
+}
+
+extern "C" {
+
+int sf_abi_version(void) { return 1; }
+const char* sf_last_error(void) { return g_err.c_str(); }
+
+void sf_default_params(sf_params* p, int rows, int cols) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->rows = rows; p->cols = cols;
+    int lv = 2, c40 = cols / 40;
+    while (c40 > 1) { c40 >>= 1; lv++; }  // log2(cols/40) + 2, FrontEnd.cpp:61
+    p->ctf_levels = lv;
+    p->max_iter_per_level = 3;   // StaticFusion-datasets.cpp:83
+    p->max_iter_irls = 6;        // :89
+    p->use_motion_filter = 1;    // :79
+    p->enable_segmentation = 1;
+    p->fovh = (float)(M_PI * 62.5 / 180.0);  // FrontEnd.cpp:57
+    p->k_photometric_res = 0.15f;            // :87
+    p->irls_delta_threshold = 0.0015f;       // :88
+    p->kc_cauchy = 0.5f; p->kb = 1.5f; p->kz = 1.5f;  // :92-94
+    p->lambda_reg = 0.35f; p->lambda_prior = 0.5f;    // :90-91
+    p->previous_speed_const_weight = 0.1f;   // :84
+    p->previous_speed_eig_weight = 2.f;      // :85
+    p->outer_exit_threshold = 0.04f;         // FrontEnd.cpp:1130
+}
+
+int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int flags) {
+    if (!out) return fail(SF_E_INVALID, "out is NULL");
+    *out = nullptr;
+    const int rc = validate(p, max_batch);
+    if (rc != SF_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SF_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SF_E_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    sf_ctx* c = new (std::nothrow) sf_ctx();
+    if (!c) return fail(SF_E_NOMEM, "host allocation failed");
+    c->p = *p; c->device = device; c->max_batch = max_batch; c->flags = flags; c->levels = p->ctf_levels;
+    fill_dev_params(c);
+    // level geometry, constants evaluated exactly as the reference does (FrontEnd.cpp:378-380, 537, 778-780, 874)
+    size_t off = 0;
+    const float th = std::tan(0.5f * p->fovh);
+    for (int l = 0; l < c->levels; l++) {
+        LevelGeom& g = c->geom[l];
+        g.rows = p->rows >> l; g.cols = p->cols >> l; g.P = g.rows * g.cols;
+        g.f = float(g.cols) / (2.f * th);
+        g.inv_f = 2.f * th / float(g.cols);
+        g.inv_f_warp = 1.f / g.f;
+        g.disp_u = 0.5f * float(g.cols - 1);
+        g.disp_v = 0.5f * float(g.rows - 1);
+        g.off = off;
+        off += (size_t)g.P;
+    }
+    Arena& a = c->a;
+    a.pyr_stride = off;
+    a.P0 = (size_t)c->geom[0].P;
+    const int F = max_batch;
+    c->n_frames_cap = 2 * F;
+    int mb = 1;
+    for (int l = 0; l < c->levels; l++) {
+        const int it = irls_chunk_iters(c->geom[l].P);
+        const int nb = (c->geom[l].P + 1024 * it - 1) / (1024 * it);
+        if (nb > mb) mb = nb;
+    }
+    a.max_blocks = mb;
+    a.trace_steps = p->ctf_levels * p->max_iter_per_level;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(SF_E_CUDA, cudaGetErrorString(e)); }
+    auto alloc = [&](void** ptr, size_t bytes) -> bool { return cudaMalloc(ptr, bytes) == cudaSuccess; };
+    bool ok = true;
+    ok = ok && alloc((void**)&a.pyr_d, sizeof(float) * a.pyr_stride * c->n_frames_cap);
+    ok = ok && alloc((void**)&a.pyr_i, sizeof(float) * a.pyr_stride * c->n_frames_cap);
+    ok = ok && alloc((void**)&c->d_cur_idx, sizeof(int) * F);
+    ok = ok && alloc((void**)&c->d_pred_idx, sizeof(int) * F);
+    ok = ok && alloc((void**)&c->d_twist_in, sizeof(float) * 6 * F);
+    ok = ok && alloc((void**)&a.labels, a.pyr_stride * F);
+    ok = ok && alloc((void**)&a.acc_d, sizeof(long long) * a.P0 * F);
+    ok = ok && alloc((void**)&a.acc_iw, sizeof(unsigned long long) * a.P0 * F);
+    ok = ok && alloc((void**)&a.warp_d, sizeof(float) * a.P0 * F);
+    ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
+    ok = ok && alloc((void**)&a.lin, sizeof(float) * NPLANES * a.P0 * F);
+    ok = ok && alloc((void**)&a.vlabel, a.P0 * F);
+    ok = ok && alloc((void**)&a.part1, sizeof(double) * 32 * a.max_blocks * F);
+    ok = ok && alloc((void**)&a.part2, sizeof(double) * a.max_blocks * F);
+    ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
+    ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
+    ok = ok && alloc((void**)&a.b_perpixel, sizeof(float) * a.P0 * F);
+    if (ok && (flags & 1)) ok = alloc((void**)&a.trace, sizeof(float) * SF_TRACE_STEP * a.trace_steps * F);
+    if (!ok) {
+        const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
+        sf_destroy(c);
+        return fail(SF_E_NOMEM, msg);
+    }
+    a.cur_idx = c->d_cur_idx; a.pred_idx = c->d_pred_idx;
+    // splat accumulators are kept zero between uses (warp_normalise clears what it reads)
+    cudaMemsetAsync(a.acc_d, 0, sizeof(long long) * a.P0 * F, c->stream);
+    cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
+    cudaMemsetAsync(a.vlabel, 0xff, a.P0 * F, c->stream);
+    cudaMemsetAsync(a.lin, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
+    c->h_out.resize(F);
+    *out = c;
+    return SF_OK;
+}
+
+void sf_destroy(sf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    Arena& a = c->a;
+    cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
+    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.lin);
+    cudaFree(a.vlabel); cudaFree(a.part1); cudaFree(a.part2); cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
+    cudaFree(a.trace);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sf_set_params(sf_ctx* c, const sf_params* p) {
+    if (!c || !p) return fail(SF_E_INVALID, "NULL argument");
+    if (p->rows != c->p.rows || p->cols != c->p.cols || p->ctf_levels != c->p.ctf_levels ||
+        p->max_iter_per_level != c->p.max_iter_per_level)
+        return fail(SF_E_INVALID, "rows, cols, ctf_levels and max_iter_per_level are fixed at sf_create");
+    if (p->max_iter_irls < 1) return fail(SF_E_INVALID, "max_iter_irls must be >= 1");
+    if (p->enable_segmentation && c->p.ctf_levels < 2) return fail(SF_E_INVALID, "segmentation needs ctf_levels >= 2");
+    c->p = *p;
+    fill_dev_params(c);
+    return SF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------------
+static int upload_stack(sf_ctx* c, float* dst_pyr, int first_frame, int frame_step, int n, const float* src, int in_space) {
+    // image k -> level-0 slot of frame first_frame + k*frame_step
+    const size_t w = sizeof(float) * c->a.P0;
+    const cudaMemcpyKind kind = (in_space == SF_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpy2DAsync(dst_pyr + (size_t)first_frame * c->a.pyr_stride, sizeof(float) * c->a.pyr_stride * frame_step, src, w, w,
+                         (size_t)n, kind, c->stream));
+    return SF_OK;
+}
+
+static int upload_twist(sf_ctx* c, int n_pairs, const float* twist_old_in) {
+    if (twist_old_in) CU(cudaMemcpyAsync(c->d_twist_in, twist_old_in, sizeof(float) * 6 * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemsetAsync(c->d_twist_in, 0, sizeof(float) * 6 * n_pairs, c->stream));
+    return SF_OK;
+}
+
+int sf_upload_pairs(sf_ctx* c, int n_pairs, const float* depth_cur, const float* inten_cur, const float* depth_pred,
+                    const float* inten_pred, int in_space, const float* twist_old_in) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (n_pairs < 1 || n_pairs > c->max_batch) return fail(SF_E_INVALID, "n_pairs must be in [1, max_batch]");
+    if (!depth_cur || !inten_cur || !depth_pred || !inten_pred) return fail(SF_E_INVALID, "NULL image pointer");
+    CU(cudaSetDevice(c->device));
+    // frames: current of pair k = 2k, prediction = 2k+1
+    int rc;
+    if ((rc = upload_stack(c, c->a.pyr_d, 0, 2, n_pairs, depth_cur, in_space))) return rc;
+    if ((rc = upload_stack(c, c->a.pyr_i, 0, 2, n_pairs, inten_cur, in_space))) return rc;
+    if ((rc = upload_stack(c, c->a.pyr_d, 1, 2, n_pairs, depth_pred, in_space))) return rc;
+    if ((rc = upload_stack(c, c->a.pyr_i, 1, 2, n_pairs, inten_pred, in_space))) return rc;
+    std::vector<int> ci(n_pairs), pi(n_pairs);
+    for (int k = 0; k < n_pairs; k++) { ci[k] = 2 * k; pi[k] = 2 * k + 1; }
+    CU(cudaMemcpyAsync(c->d_cur_idx, ci.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // ci/pi are stack-lifetime host buffers
+    c->n_pairs = n_pairs; c->n_frames = 2 * n_pairs; c->uploaded = true; c->solved = false;
+    return SF_OK;
+}
+
+int sf_upload_sequence(sf_ctx* c, int n_frames, const float* depth, const float* inten, int in_space, const float* twist_old_in) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (n_frames < 2 || n_frames - 1 > c->max_batch) return fail(SF_E_INVALID, "n_frames-1 must be in [1, max_batch]");
+    if (!depth || !inten) return fail(SF_E_INVALID, "NULL image pointer");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload_stack(c, c->a.pyr_d, 0, 1, n_frames, depth, in_space))) return rc;
+    if ((rc = upload_stack(c, c->a.pyr_i, 0, 1, n_frames, inten, in_space))) return rc;
+    const int n_pairs = n_frames - 1;
+    std::vector<int> ci(n_pairs), pi(n_pairs);
+    for (int k = 0; k < n_pairs; k++) { ci[k] = k + 1; pi[k] = k; }  // prediction := previous raw frame
+    CU(cudaMemcpyAsync(c->d_cur_idx, ci.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_pairs = n_pairs; c->n_frames = n_frames; c->uploaded = true; c->solved = false;
+    return SF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule
+// ---------------------------------------------------------------------------------------------
+static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
+    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames};
+    const Arena& a = c->a;
+    const DevParams& dp = c->dp;
+    int n = 0;
+    n += launch_init_pairs(a, dp, c->d_twist_in, cfg);
+    if (build_pyramids) n += launch_pyramids(a, c->geom, c->levels, cfg);
+    n += launch_kmeans(a, dp, c->geom, c->levels, cfg);
+    bool stop = false;
+    for (int i = 0; i < c->levels && !stop; i++)
+        for (int k = 0; k < c->p.max_iter_per_level && !stop; k++) {
+            const int image_level = c->levels - i - 1;  // FrontEnd.cpp:1100
+            const LevelGeom& g = c->geom[image_level];
+            const int first = (i == 0 && k == 0) ? 1 : 0;
+            n += launch_step_begin(a, i, k, cfg);
+            if (!first) n += launch_warp(a, g, cfg);
+            n += launch_linearise(a, dp, g, first, cfg);
+            n += launch_step_prep(a, dp, i, k, cfg);
+            if (i * c->p.max_iter_per_level + k == c->stop_step) { stop = true; break; }
+            for (int it = 1; it <= c->p.max_iter_irls; it++) n += launch_irls_iteration(a, dp, g, i, k, it, cfg);
+            n += launch_pose_update(a, dp, i, k, cfg);
+        }
+    n += launch_finish(a, dp, c->geom[0], cfg);
+    c->launches = n;
+    CU(cudaGetLastError());
+    return SF_OK;
+}
+
+int sf_launch(sf_ctx* c) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->uploaded) return fail(SF_E_STATE, "no batch uploaded");
+    CU(cudaSetDevice(c->device));
+    const int rc = enqueue_solve(c, true);
+    if (rc == SF_OK) c->solved = true;
+    return rc;
+}
+
+int sf_sync(sf_ctx* c) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+uint64_t sf_stream(sf_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+int sf_last_launch_count(sf_ctx* c) { return c ? c->launches : 0; }
+
+int sf_download(sf_ctx* c, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel, uint8_t* labels_u8,
+                int out_space, int* irls_iters, int* status) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    CU(cudaSetDevice(c->device));
+    const int n = c->n_pairs;
+    CU(cudaMemcpyAsync(c->h_out.data(), c->a.out, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    const cudaMemcpyKind kind = (out_space == SF_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, c->a.b_perpixel, sizeof(float) * c->a.P0 * n, kind, c->stream));
+    if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, c->a.P0, c->a.labels, c->a.pyr_stride, c->a.P0, (size_t)n, kind, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; k++) {
+        const PairOut& o = c->h_out[k];
+        if (T_odometry)
+            for (int r = 0; r < 4; r++)
+                for (int q = 0; q < 4; q++) T_odometry[k * 16 + q * 4 + r] = o.T[r * 4 + q];  // row-major -> Eigen column-major
+        if (twist_old_out) std::memcpy(twist_old_out + k * 6, o.twist_old, sizeof(float) * 6);
+        if (b_segm) std::memcpy(b_segm + k * NC, o.b_segm, sizeof(float) * NC);
+        if (irls_iters) irls_iters[k] = o.irls_iters;
+        if (status) status[k] = o.status;
+    }
+    return SF_OK;
+}
+
+int sf_solve_batch(sf_ctx* c, int n_pairs, const float* depth_cur, const float* inten_cur, const float* depth_pred,
+                   const float* inten_pred, int in_space, const float* twist_old_in, float* T_odometry, float* twist_old_out,
+                   float* b_segm, float* b_perpixel, uint8_t* labels_u8, int out_space, int* irls_iters, int* status) {
+    int rc = sf_upload_pairs(c, n_pairs, depth_cur, inten_cur, depth_pred, inten_pred, in_space, twist_old_in);
+    if (rc) return rc;
+    if ((rc = sf_launch(c))) return rc;
+    return sf_download(c, T_odometry, twist_old_out, b_segm, b_perpixel, labels_u8, out_space, irls_iters, status);
+}
+
+int sf_solve_sequence(sf_ctx* c, int n_frames, const float* depth, const float* inten, int in_space, const float* twist_old_in,
+                      float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel, uint8_t* labels_u8,
+                      int out_space, int* irls_iters, int* status) {
+    int rc = sf_upload_sequence(c, n_frames, depth, inten, in_space, twist_old_in);
+    if (rc) return rc;
+    if ((rc = sf_launch(c))) return rc;
+    return sf_download(c, T_odometry, twist_old_out, b_segm, b_perpixel, labels_u8, out_space, irls_iters, status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// drop-in trio (one pair, host buffers, reference call order)
+// ---------------------------------------------------------------------------------------------
+static void to_row_major(const float* src, float* dst, int rows, int cols, int col_major) {
+    if (!col_major) { std::memcpy(dst, src, sizeof(float) * rows * cols); return; }
+    for (int v = 0; v < rows; v++)
+        for (int u = 0; u < cols; u++) dst[(size_t)v * cols + u] = src[(size_t)u * rows + v];
+}
+
+int sf_set_current(sf_ctx* c, const float* depth, const float* intensity, int col_major) {
+    if (!c || !depth || !intensity) return fail(SF_E_INVALID, "NULL argument");
+    const size_t n = c->a.P0;
+    c->h_cur_d.resize(n); c->h_cur_i.resize(n);
+    to_row_major(depth, c->h_cur_d.data(), c->p.rows, c->p.cols, col_major);
+    to_row_major(intensity, c->h_cur_i.data(), c->p.rows, c->p.cols, col_major);
+    c->have_cur = true;
+    return SF_OK;
+}
+
+int sf_set_prediction(sf_ctx* c, const float* depth, const float* intensity, int col_major) {
+    if (!c || !depth || !intensity) return fail(SF_E_INVALID, "NULL argument");
+    const size_t n = c->a.P0;
+    c->h_pred_d.resize(n); c->h_pred_i.resize(n);
+    to_row_major(depth, c->h_pred_d.data(), c->p.rows, c->p.cols, col_major);
+    to_row_major(intensity, c->h_pred_i.data(), c->p.rows, c->p.cols, col_major);
+    c->have_pred = true;
+    c->trio_pyr_pred = false;
+    return SF_OK;
+}
+
+int sf_set_twist_old(sf_ctx* c, const float t[6]) {
+    if (!c || !t) return fail(SF_E_INVALID, "NULL argument");
+    std::memcpy(c->h_twist_old, t, sizeof(float) * 6);
+    return SF_OK;
+}
+
+int sf_create_image_pyramid(sf_ctx* c, int old_im) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    // frame slot 0 = current, 1 = prediction (pair 0)
+    const int frame = old_im ? 1 : 0;
+    if (old_im ? !c->have_pred : !c->have_cur) return fail(SF_E_STATE, "input images were not set");
+    const float* d = old_im ? c->h_pred_d.data() : c->h_cur_d.data();
+    const float* i = old_im ? c->h_pred_i.data() : c->h_cur_i.data();
+    int rc;
+    if ((rc = upload_stack(c, c->a.pyr_d, frame, 1, 1, d, SF_MEM_HOST))) return rc;
+    if ((rc = upload_stack(c, c->a.pyr_i, frame, 1, 1, i, SF_MEM_HOST))) return rc;
+    // build this frame's pyramid only: temporarily view the arena from `frame`
+    Arena a = c->a;
+    a.pyr_d += (size_t)frame * a.pyr_stride;
+    a.pyr_i += (size_t)frame * a.pyr_stride;
+    const LaunchCfg cfg{c->stream, 1, 1};
+    launch_pyramids(a, c->geom, c->levels, cfg);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    if (old_im) c->trio_pyr_pred = true;
+    return SF_OK;
+}
+
+int sf_run_solver(sf_ctx* c, int create_image_pyr) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->have_cur || !c->have_pred) return fail(SF_E_STATE, "input images were not set");
+    if (!c->trio_pyr_pred) return fail(SF_E_STATE, "createImagePyramid(true) must run before runSolver (StaticFusion-datasets.cpp:171-173)");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if (create_image_pyr) {
+        if ((rc = sf_create_image_pyramid(c, 0))) return rc;
+    }
+    const int ci = 0, pi = 1;
+    CU(cudaMemcpyAsync(c->d_cur_idx, &ci, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pred_idx, &pi, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_twist_in, c->h_twist_old, sizeof(float) * 6, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_pairs = 1; c->n_frames = 2; c->uploaded = true;
+    rc = enqueue_solve(c, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->solved = true;
+    return SF_OK;
+}
+
+int sf_build_segm_image(sf_ctx* c) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->solved) return fail(SF_E_STATE, "runSolver has not run");
+    // the per-pixel image is produced at the end of every solve (segm_image_kernel); nothing left to do
+    return SF_OK;
+}
+
+int sf_get_outputs(sf_ctx* c, float T_odometry[16], float twist_old_out[6], float b_segm[SF_NUM_CLUSTERS], float* b_perpixel,
+                   int32_t* labels, int col_major, int* irls_iterations, int* status) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->solved) return fail(SF_E_STATE, "runSolver has not run");
+    const int rows = c->p.rows, cols = c->p.cols;
+    const size_t n = c->a.P0;
+    std::vector<float> bp(b_perpixel ? n : 0);
+    std::vector<uint8_t> lb(labels ? n : 0);
+    const int rc = sf_download(c, T_odometry, twist_old_out, b_segm, b_perpixel ? bp.data() : nullptr, labels ? lb.data() : nullptr,
+                               SF_MEM_HOST, irls_iterations, status);
+    if (rc) return rc;
+    for (int v = 0; v < rows; v++)
+        for (int u = 0; u < cols; u++) {
+            const size_t src = (size_t)v * cols + u;
+            const size_t dst = col_major ? (size_t)u * rows + v : src;
+            if (b_perpixel) b_perpixel[dst] = bp[src];
+            if (labels) labels[dst] = (int32_t)lb[src];
+        }
+    return SF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+int sf_debug_set_stop_step(sf_ctx* c, int stop_step) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    c->stop_step = stop_step;
+    return SF_OK;
+}
+
+int sf_debug_get_plane(sf_ctx* c, const char* name, int pair, int image_level, float* out) {
+    if (!c || !name || !out) return fail(SF_E_INVALID, "NULL argument");
+    if (pair < 0 || pair >= c->n_pairs || image_level < 0 || image_level >= c->levels) return fail(SF_E_INVALID, "pair / level out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const LevelGeom& g = c->geom[image_level];
+    const Arena& a = c->a;
+    int ci = 0, pi = 0;
+    CU(cudaMemcpy(&ci, c->d_cur_idx + pair, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&pi, c->d_pred_idx + pair, sizeof(int), cudaMemcpyDeviceToHost));
+    const std::string n(name);
+    const float* src = nullptr;
+    if (n == "depth") src = a.pyr_d + (size_t)ci * a.pyr_stride + g.off;
+    else if (n == "intensity") src = a.pyr_i + (size_t)ci * a.pyr_stride + g.off;
+    else if (n == "depth_pred") src = a.pyr_d + (size_t)pi * a.pyr_stride + g.off;
+    else if (n == "intensity_pred") src = a.pyr_i + (size_t)pi * a.pyr_stride + g.off;
+    else if (n == "depth_warped") src = a.warp_d + (size_t)pair * a.P0;
+    else if (n == "intensity_warped") src = a.warp_i + (size_t)pair * a.P0;
+    else {
+        static const char* names[NPLANES] = {"depth_inter", "xx_inter", "yy_inter", "dcu", "dcv", "dct", "ddu", "ddv", "ddt", "weights_c", "weights_d"};
+        for (int k = 0; k < NPLANES; k++)
+            if (n == names[k]) src = a.lin + ((size_t)pair * NPLANES + k) * a.P0;
+    }
+    if (src) {
+        CU(cudaMemcpy(out, src, sizeof(float) * g.P, cudaMemcpyDeviceToHost));
+        return SF_OK;
+    }
+    if (n == "valid") {
+        std::vector<uint8_t> v(g.P);
+        CU(cudaMemcpy(v.data(), a.vlabel + (size_t)pair * a.P0, g.P, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < g.P; i++) out[i] = (v[i] != VLABEL_INVALID) ? 1.f : 0.f;
+        return SF_OK;
+    }
+    return fail(SF_E_INVALID, "unknown plane name");
+}
+
+int sf_debug_get_labels(sf_ctx* c, int pair, int image_level, int32_t* out) {
+    if (!c || !out) return fail(SF_E_INVALID, "NULL argument");
+    if (pair < 0 || pair >= c->n_pairs || image_level < 0 || image_level >= c->levels) return fail(SF_E_INVALID, "pair / level out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const LevelGeom& g = c->geom[image_level];
+    std::vector<uint8_t> v(g.P);
+    CU(cudaMemcpy(v.data(), c->a.labels + (size_t)pair * c->a.pyr_stride + g.off, g.P, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < g.P; i++) out[i] = v[i];
+    return SF_OK;
+}
+
+int sf_debug_get_kmeans(sf_ctx* c, int pair, float centres[3 * SF_NUM_CLUSTERS], uint8_t connectivity[SF_NUM_CLUSTERS * SF_NUM_CLUSTERS]) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (pair < 0 || pair >= c->n_pairs) return fail(SF_E_INVALID, "pair out of range");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    PairCtl h;
+    CU(cudaMemcpy(&h, c->a.ctl + pair, sizeof(PairCtl), cudaMemcpyDeviceToHost));
+    if (centres) std::memcpy(centres, h.kmeans, sizeof(float) * 3 * NC);
+    if (connectivity)
+        for (int i = 0; i < NC; i++)
+            for (int j = 0; j < NC; j++) connectivity[i * NC + j] = (h.conn[i] >> j) & 1u;
+    return SF_OK;
+}
+
+int sf_debug_get_trace(sf_ctx* c, int pair, float* out, int n_floats) {
+    if (!c || !out) return fail(SF_E_INVALID, "NULL argument");
+    if (!c->a.trace) return fail(SF_E_STATE, "context was created without the trace flag");
+    if (pair < 0 || pair >= c->n_pairs) return fail(SF_E_INVALID, "pair out of range");
+    const int need = c->a.trace_steps * SF_TRACE_STEP;
+    if (n_floats < need) return fail(SF_E_INVALID, "trace buffer too small");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->a.trace + (size_t)pair * need, sizeof(float) * need, cudaMemcpyDeviceToHost));
+    return SF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// sf_kernels.cuh — launch interface between the C ABI (sf_api.cu) and the kernels (sf_kernels.cu).
+#pragma once
+#include "sf_device.cuh"
+
+namespace sf {
+
+// compact per-pair result block copied back to the host
+struct PairOut {
+    float T[16];        // row-major
+    float twist_old[6]; // after FrontEnd.cpp:1143-1144
+    float b_segm[NC];
+    int irls_iters;
+    int status;
+};
+
+// device arena: base pointers + strides, passed to kernels by value
+struct Arena {
+    // image pyramids, one per frame: [n_frames][pyr_stride]
+    float* pyr_d;
+    float* pyr_i;
+    size_t pyr_stride;  // pixels per pyramid (sum over levels)
+    // pair -> frame indices
+    const int* cur_idx;
+    const int* pred_idx;
+    // per pair
+    uint8_t* labels;            // [F][pyr_stride] cluster labels, 24 = no depth
+    long long* acc_d;           // [F][P0] warp depth accumulator (fixed point 2^32)
+    unsigned long long* acc_iw; // [F][P0] packed: weight sum (high 22 bits) | intensity sum (low 42 bits, 2^22)
+    float* warp_d;              // [F][P0]
+    float* warp_i;              // [F][P0]
+    float* lin;                 // [F][NPLANES][P0]
+    uint8_t* vlabel;            // [F][P0]
+    double* part1;              // [F][max_blocks][32]
+    double* part2;              // [F][max_blocks]
+    PairCtl* ctl;               // [F]
+    PairOut* out;               // [F]
+    float* b_perpixel;          // [F][P0]
+    float* trace;               // [F][steps][SF_TRACE_STEP] or nullptr
+    size_t P0;                  // pixels of level 0
+    int max_blocks;
+    int trace_steps;
+};
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int n_pairs;
+    int n_frames;
+};
+
+int irls_chunk_iters(int P);  // deterministic function of the level size only
+
+// every launcher returns the number of kernels it enqueued
+int launch_init_pairs(const Arena& a, const DevParams& p, const float* twist_old_in_dev, const LaunchCfg& c);
+int launch_pyramids(const Arena& a, const LevelGeom* geom, int levels, const LaunchCfg& c);
+int launch_kmeans(const Arena& a, const DevParams& p, const LevelGeom* geom, int levels, const LaunchCfg& c);
+int launch_step_begin(const Arena& a, int level_i, int k, const LaunchCfg& c);
+int launch_warp(const Arena& a, const LevelGeom& g, const LaunchCfg& c);
+int launch_linearise(const Arena& a, const DevParams& p, const LevelGeom& g, int first, const LaunchCfg& c);
+int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
+int launch_irls_iteration(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
+int launch_pose_update(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
+int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const LaunchCfg& c);
+
+}  // namespace sf

@@ -1,0 +1,229 @@
+"""Python face of the C ABI: the same calls, names and argument meaning as the reference object.
+
+``StaticFusionSolver`` mirrors ``class StaticFusion`` (reference ``StaticFusion.h:66-189``) for the
+one path this project replaces: the fields a driver writes (``depthCurrent`` …), the three methods
+it calls (``createImagePyramid``, ``runSolver``, ``buildSegmImage``) and the fields it reads
+(``T_odometry``, ``b_segm_perpixel``, ``clusterAllocation[0]``), plus the batched entry points that
+shard frame pairs over GPUs.  All compute happens inside libstaticfusion_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, NUM_CLUSTERS, TRACE_STEP, SfParams, check
+
+
+def default_params(rows: int = 240, cols: int = 320, **overrides) -> SfParams:
+    """Driver parameter block (reference ``StaticFusion-datasets.cpp:79-94``); keyword overrides by field name."""
+    p = SfParams()
+    _lib.lib().sf_default_params(C.byref(p), rows, cols)
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _addr(x):
+    """(address, memspace, keepalive) of a numpy array or a CUDA torch tensor holding float32 images."""
+    if isinstance(x, np.ndarray):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        return a.ctypes.data, MEM_HOST, a
+    # torch tensor
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if x.dtype.__str__() != "torch.float32":
+        raise TypeError("images must be float32")
+    return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST), x
+
+
+class BatchResult:
+    __slots__ = ("T", "twist_old", "b_segm", "b_perpixel", "labels", "irls_iters", "status")
+
+    def __init__(self, n, rows, cols, want_images):
+        self.T = np.zeros((n, 16), np.float32)  # column-major 4x4 each (Eigen::Matrix4f)
+        self.twist_old = np.zeros((n, 6), np.float32)
+        self.b_segm = np.zeros((n, NUM_CLUSTERS), np.float32)
+        self.b_perpixel = np.zeros((n, rows, cols), np.float32) if want_images else None
+        self.labels = np.zeros((n, rows, cols), np.uint8) if want_images else None
+        self.irls_iters = np.zeros(n, np.int32)
+        self.status = np.zeros(n, np.int32)
+
+    def T_matrices(self):
+        """(n,4,4) row-major numpy view of the increments (T_odometry as a math matrix)."""
+        return self.T.reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+class StaticFusionSolver:
+    """B200 solver context.  One instance per host thread / GPU (like the single-threaded reference object)."""
+
+    def __init__(self, params: SfParams | None = None, device: int = 0, max_batch: int = 1, trace: bool = False):
+        self.L = _lib.lib()
+        self.params = params if params is not None else default_params()
+        self.rows, self.cols = self.params.rows, self.params.cols
+        self.max_batch = max_batch
+        h = C.c_void_p()
+        check(self.L.sf_create(C.byref(h), C.byref(self.params), device, max_batch, 1 if trace else 0))
+        self.h = h
+        # drop-in fields (reference names)
+        self.depthCurrent = self.intensityCurrent = self.depthPrediction = self.intensityPrediction = None
+        self.twist_odometry_old = np.zeros(6, np.float32)
+        self.T_odometry = np.eye(4, dtype=np.float32)
+        self.b_segm = np.full(NUM_CLUSTERS, 0.5, np.float32)
+        self.b_segm_perpixel = np.full((self.rows, self.cols), 0.5, np.float32)
+        self.clusterAllocation0 = np.zeros((self.rows, self.cols), np.int32)
+        self.irls_iterations = 0
+        self.status = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params: SfParams):
+        check(self.L.sf_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    # ---- the reference's call sequence (StaticFusion-datasets.cpp:171-190), one pair, host buffers ----
+    def createImagePyramid(self, old_im: bool):
+        if old_im:
+            d, i = (np.ascontiguousarray(x, np.float32) for x in (self.depthPrediction, self.intensityPrediction))
+            check(self.L.sf_set_prediction(self.h, _fp(d), _fp(i), 0))
+        else:
+            d, i = (np.ascontiguousarray(x, np.float32) for x in (self.depthCurrent, self.intensityCurrent))
+            check(self.L.sf_set_current(self.h, _fp(d), _fp(i), 0))
+        check(self.L.sf_create_image_pyramid(self.h, int(old_im)))
+
+    def runSolver(self, create_image_pyr: bool = True):
+        if create_image_pyr:
+            d, i = (np.ascontiguousarray(x, np.float32) for x in (self.depthCurrent, self.intensityCurrent))
+            check(self.L.sf_set_current(self.h, _fp(d), _fp(i), 0))
+        t = np.ascontiguousarray(self.twist_odometry_old, np.float32)
+        check(self.L.sf_set_twist_old(self.h, _fp(t)))
+        check(self.L.sf_run_solver(self.h, int(create_image_pyr)))
+        T = np.zeros(16, np.float32)
+        tw = np.zeros(6, np.float32)
+        b = np.zeros(NUM_CLUSTERS, np.float32)
+        it, st = C.c_int(0), C.c_int(0)
+        check(self.L.sf_get_outputs(self.h, _fp(T), _fp(tw), _fp(b), None, None, 0, C.byref(it), C.byref(st)))
+        self.T_odometry = T.reshape(4, 4).T.copy()  # column-major buffer -> math matrix
+        self.twist_odometry_old = tw
+        self.b_segm = b
+        self.irls_iterations, self.status = it.value, st.value
+
+    def buildSegmImage(self):
+        check(self.L.sf_build_segm_image(self.h))
+        bp = np.zeros((self.rows, self.cols), np.float32)
+        lb = np.zeros((self.rows, self.cols), np.int32)
+        check(self.L.sf_get_outputs(self.h, None, None, None, _fp(bp), lb.ctypes.data_as(C.POINTER(C.c_int32)), 0, None, None))
+        self.b_segm_perpixel, self.clusterAllocation0 = bp, lb
+
+    # ---- batched path ----
+    def solve_batch(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None, want_images=True) -> BatchResult:
+        n = int(depth_cur.shape[0])
+        a = [_addr(x) for x in (depth_cur, inten_cur, depth_pred, inten_pred)]
+        space = a[0][1]
+        if any(s != space for _, s, _ in a):
+            raise ValueError("all image stacks must live in the same memory space")
+        r = BatchResult(n, self.rows, self.cols, want_images)
+        tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        check(self.L.sf_solve_batch(
+            self.h, n, a[0][0], a[1][0], a[2][0], a[3][0], space, None if tw is None else _fp(tw),
+            _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
+            r.b_perpixel.ctypes.data if want_images else None, r.labels.ctypes.data if want_images else None, MEM_HOST,
+            _ip(r.irls_iters), _ip(r.status)))
+        return r
+
+    def solve_sequence(self, depth, inten, twist_old=None, want_images=True) -> BatchResult:
+        nf = int(depth.shape[0])
+        a = [_addr(x) for x in (depth, inten)]
+        if a[0][1] != a[1][1]:
+            raise ValueError("all image stacks must live in the same memory space")
+        r = BatchResult(nf - 1, self.rows, self.cols, want_images)
+        tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        check(self.L.sf_solve_sequence(
+            self.h, nf, a[0][0], a[1][0], a[0][1], None if tw is None else _fp(tw),
+            _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
+            r.b_perpixel.ctypes.data if want_images else None, r.labels.ctypes.data if want_images else None, MEM_HOST,
+            _ip(r.irls_iters), _ip(r.status)))
+        return r
+
+    # ---- split phase (benchmark) ----
+    def upload_pairs(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None):
+        n = int(depth_cur.shape[0])
+        a = [_addr(x) for x in (depth_cur, inten_cur, depth_pred, inten_pred)]
+        tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        check(self.L.sf_upload_pairs(self.h, n, a[0][0], a[1][0], a[2][0], a[3][0], a[0][1], None if tw is None else _fp(tw)))
+        self._n = n
+
+    def upload_sequence(self, depth, inten, twist_old=None):
+        nf = int(depth.shape[0])
+        a = [_addr(x) for x in (depth, inten)]
+        tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        check(self.L.sf_upload_sequence(self.h, nf, a[0][0], a[1][0], a[0][1], None if tw is None else _fp(tw)))
+        self._n = nf - 1
+
+    def launch(self):
+        check(self.L.sf_launch(self.h))
+
+    def sync(self):
+        check(self.L.sf_sync(self.h))
+
+    def download(self, want_images=False) -> BatchResult:
+        r = BatchResult(self._n, self.rows, self.cols, want_images)
+        check(self.L.sf_download(
+            self.h, _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
+            r.b_perpixel.ctypes.data if want_images else None, r.labels.ctypes.data if want_images else None, MEM_HOST,
+            _ip(r.irls_iters), _ip(r.status)))
+        return r
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.sf_stream(self.h))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.L.sf_last_launch_count(self.h))
+
+    # ---- introspection (parity tests) ----
+    def debug_set_stop_step(self, step: int):
+        check(self.L.sf_debug_set_stop_step(self.h, step))
+
+    def debug_plane(self, name: str, pair: int, level: int) -> np.ndarray:
+        out = np.zeros((self.rows >> level, self.cols >> level), np.float32)
+        check(self.L.sf_debug_get_plane(self.h, name.encode(), pair, level, _fp(out)))
+        return out
+
+    def debug_labels(self, pair: int, level: int) -> np.ndarray:
+        out = np.zeros((self.rows >> level, self.cols >> level), np.int32)
+        check(self.L.sf_debug_get_labels(self.h, pair, level, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def debug_kmeans(self, pair: int):
+        cen = np.zeros((3, NUM_CLUSTERS), np.float32)
+        conn = np.zeros((NUM_CLUSTERS, NUM_CLUSTERS), np.uint8)
+        check(self.L.sf_debug_get_kmeans(self.h, pair, _fp(cen), conn.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return cen, conn
+
+    def debug_trace(self, pair: int) -> np.ndarray:
+        n = self.params.ctf_levels * self.params.max_iter_per_level * TRACE_STEP
+        out = np.zeros(n, np.float32)
+        check(self.L.sf_debug_get_trace(self.h, pair, _fp(out), n))
+        return out.reshape(-1, TRACE_STEP)
