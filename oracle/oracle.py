@@ -22,6 +22,7 @@ TRACE_IRLS = 34
 TRACE_STEP = TRACE_HDR + TRACE_MAX_IRLS * TRACE_IRLS
 ACCUM_F32 = 0
 ACCUM_EXACT = 1
+ACCUM_F64 = 2
 
 
 class Params(C.Structure):

@@ -58,6 +58,21 @@ inline float sq(float x) { return x * x; }
 inline int64_t fixq(float x, int s) { return (int64_t)llrintf(ldexpf(x, s)); }
 inline double fixval(int64_t acc, int s) { return std::ldexp((double)acc, -s); }
 
+/* EXACT policy for the normal equations and |res|^2: every column of the weighted system is scaled by a
+ * power of two so that its magnitude stays below 2^10, each product is rounded to the nearest integer
+ * (round-half-even of the exact product, which is what fmaf(a, b, 1.5*2^23) - 1.5*2^23 yields on the GPU)
+ * and the integers are summed: associative, hence independent of the reduction order. */
+inline int scale_exponent(float bound) {
+    if (!(bound > 0.f) || !std::isfinite(bound)) return 0;
+    int e;
+    (void)frexpf(bound, &e); /* bound = m * 2^e, m in [0.5, 1) */
+    int s = 10 - e;
+    if (s > 100) s = 100;
+    if (s < -100) s = -100;
+    return s;
+}
+inline int64_t qprod(float a, float b) { return (int64_t)std::nearbyint((double)a * (double)b); }
+
 /* =====================================================================================
  * Small dense algebra (templated on float / double)
  * ===================================================================================== */
@@ -643,7 +658,7 @@ void orc_ctx::warpImagesAccurateInverse() {
     std::vector<float> wacu(np, 0.f);
     std::vector<int64_t> dfix, ifix;
     std::vector<int32_t> wfix;
-    const bool exact = (accum == ORC_ACCUM_EXACT);
+    const bool exact = (accum != ORC_ACCUM_F32);
     if (exact) { dfix.assign(np, 0); ifix.assign(np, 0); wfix.assign(np, 0); }
     const int cols_lim = 100 * (cols_i - 1);
     const int rows_lim = 100 * (rows_i - 1);
@@ -930,7 +945,8 @@ void orc_ctx::solveOdometryAndSegmJoint() {
     const Img& xx_inter_ref = xxInterPyr[image_level];
     const Img& yy_inter_ref = yyInterPyr[image_level];
     const size_t N = validPixels.size();
-    const bool exact = (accum == ORC_ACCUM_EXACT);
+    const bool exact = (accum != ORC_ACCUM_F32);   /* fixed-point bounded sums + double algebra */
+    const bool quant = (accum == ORC_ACCUM_EXACT); /* integer normal equations and |res|^2 (the CUDA contract) */
     float* tr = cur_trace;
     tr[3] = (float)N;
     tr[5] = max_wc_raw; tr[6] = max_wd_raw;
@@ -945,48 +961,60 @@ void orc_ctx::solveOdometryAndSegmJoint() {
     std::vector<float> A(2 * N * 6), B(2 * N), res(2 * N);
     std::vector<int> lab(N);
     const float f_inv = float(cols_i) / (2.f * std::tan(0.5f * p.fovh));
-    size_t cont = 0;
-    int64_t fixBc = 0, fixBd = 0;
-    for (size_t n = 0; n < N; n++) {
-        const int v = validPixels[n].first, u = validPixels[n].second;
-        lab[n] = p.enable_segmentation ? labels_ref(v, u) : 0;
+    /* the two Jacobian rows of a pixel, :545-585; wc_n / wd_n are the (normalised) pre-weights */
+    auto build_rows = [&](int v, int u, float wc_n, float wd_n, float* ac, float& bc, float* ad, float& bd) {
         const float d = depth_inter_ref(v, u);
         const float inv_d = 1.f / d;
         const float x = xx_inter_ref(v, u);
         const float y = yy_inter_ref(v, u);
-        const float wc_n = inv_max_c * weights_c(v, u); /* :505-509 */
-        const float wd_n = inv_max_d * weights_d(v, u);
-        /* colour, :552-566 */
         const float dycomp_c = dcu(v, u) * f_inv * inv_d;
         const float dzcomp_c = dcv(v, u) * f_inv * inv_d;
         const float twc = wc_n * p.k_photometric_res;
-        float* a = &A[cont * 6];
-        a[0] = twc * (-dycomp_c);
-        a[1] = twc * (-dzcomp_c);
-        a[2] = twc * (dycomp_c * x * inv_d + dzcomp_c * y * inv_d);
-        a[3] = twc * (dycomp_c * inv_d * y * x + dzcomp_c * (y * y * inv_d + d));
-        a[4] = twc * (-dycomp_c * (x * x * inv_d + d) - dzcomp_c * inv_d * y * x);
-        a[5] = twc * (dycomp_c * y - dzcomp_c * x);
-        B[cont] = twc * (-dct(v, u));
-        cont++;
-        /* geometry, :570-585 */
+        ac[0] = twc * (-dycomp_c);
+        ac[1] = twc * (-dzcomp_c);
+        ac[2] = twc * (dycomp_c * x * inv_d + dzcomp_c * y * inv_d);
+        ac[3] = twc * (dycomp_c * inv_d * y * x + dzcomp_c * (y * y * inv_d + d));
+        ac[4] = twc * (-dycomp_c * (x * x * inv_d + d) - dzcomp_c * inv_d * y * x);
+        ac[5] = twc * (dycomp_c * y - dzcomp_c * x);
+        bc = twc * (-dct(v, u));
         const float dycomp_d = ddu(v, u) * f_inv * inv_d;
         const float dzcomp_d = ddv(v, u) * f_inv * inv_d;
         const float twd = wd_n;
-        a = &A[cont * 6];
-        a[0] = twd * (-dycomp_d);
-        a[1] = twd * (-dzcomp_d);
-        a[2] = twd * (1.f + dycomp_d * x * inv_d + dzcomp_d * y * inv_d);
-        a[3] = twd * (y + dycomp_d * inv_d * y * x + dzcomp_d * (y * y * inv_d + d));
-        a[4] = twd * (-x - dycomp_d * (x * x * inv_d + d) - dzcomp_d * inv_d * y * x);
-        a[5] = twd * (dycomp_d * y - dzcomp_d * x);
-        B[cont] = twd * (-ddt(v, u));
-        cont++;
+        ad[0] = twd * (-dycomp_d);
+        ad[1] = twd * (-dzcomp_d);
+        ad[2] = twd * (1.f + dycomp_d * x * inv_d + dzcomp_d * y * inv_d);
+        ad[3] = twd * (y + dycomp_d * inv_d * y * x + dzcomp_d * (y * y * inv_d + d));
+        ad[4] = twd * (-x - dycomp_d * (x * x * inv_d + d) - dzcomp_d * inv_d * y * x);
+        ad[5] = twd * (dycomp_d * y - dzcomp_d * x);
+        bd = twd * (-ddt(v, u));
+    };
+    size_t cont = 0;
+    int64_t fixBc = 0, fixBd = 0;
+    float Mc[7] = {0, 0, 0, 0, 0, 0, 0}, Md[7] = {0, 0, 0, 0, 0, 0, 0}; /* column maxima of the rows built with raw weights */
+    for (size_t n = 0; n < N; n++) {
+        const int v = validPixels[n].first, u = validPixels[n].second;
+        lab[n] = p.enable_segmentation ? labels_ref(v, u) : 0;
+        const float wc_n = inv_max_c * weights_c(v, u); /* :505-509 */
+        const float wd_n = inv_max_d * weights_d(v, u);
+        build_rows(v, u, wc_n, wd_n, &A[cont * 6], B[cont], &A[(cont + 1) * 6], B[cont + 1]);
+        cont += 2;
         if (exact) {
             fixBc += fixq(weights_c(v, u) * std::fabs(dct(v, u)), 32);
             fixBd += fixq(weights_d(v, u) * std::fabs(ddt(v, u)), 32);
+            float ac[6], ad[6], bc, bd;
+            build_rows(v, u, weights_c(v, u), weights_d(v, u), ac, bc, ad, bd);
+            for (int c = 0; c < 6; c++) { Mc[c] = std::max(Mc[c], std::fabs(ac[c])); Md[c] = std::max(Md[c], std::fabs(ad[c])); }
+            Mc[6] = std::max(Mc[6], std::fabs(bc)); Md[6] = std::max(Md[6], std::fabs(bd));
         }
     }
+    /* power-of-two column scales of the EXACT policy */
+    int sexp[7] = {0, 0, 0, 0, 0, 0, 0};
+    float colbound[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (exact)
+        for (int c = 0; c < 7; c++) {
+            colbound[c] = std::max(inv_max_c * Mc[c], inv_max_d * Md[c]);
+            sexp[c] = scale_exponent(colbound[c]);
+        }
     /* :589-590 */
     float aver_res;
     if (!exact) {
@@ -1017,8 +1045,9 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         for (int i = 0; i < 36; i++) AtA[i] = 0;
         for (int i = 0; i < 6; i++) AtB[i] = 0;
         float AtAf[36], AtBf[6];
-        for (int i = 0; i < 36; i++) AtAf[i] = 0.f;
-        for (int i = 0; i < 6; i++) AtBf[i] = 0.f;
+        int64_t AtAq[36], AtBq[6];
+        for (int i = 0; i < 36; i++) { AtAf[i] = 0.f; AtAq[i] = 0; }
+        for (int i = 0; i < 6; i++) { AtBf[i] = 0.f; AtBq[i] = 0; }
         for (size_t n = 0; n < N; n++) {
             const float b_weight = std::max(0.f, std::min(1.f, b_segm[lab[n]]));
             for (int r = 0; r < 2; r++) { /* :627-636 */
@@ -1027,7 +1056,19 @@ void orc_ctx::solveOdometryAndSegmJoint() {
                 float aw[6];
                 for (int c = 0; c < 6; c++) aw[c] = w * A[row * 6 + c];
                 const float bw = w * B[row];
-                if (exact) {
+                if (quant) {
+                    float aws[6];
+                    for (int c = 0; c < 6; c++) aws[c] = ldexpf(aw[c], sexp[c]);
+                    const float bws = ldexpf(bw, sexp[6]);
+                    for (int i = 0; i < 6; i++) {
+                        for (int j = i; j < 6; j++) {
+                            const int64_t q = qprod(aws[i], aws[j]);
+                            if (q > 2097152 || q < -2097152) status |= 8; /* scale bound violated: must never happen */
+                            AtAq[i * 6 + j] += q;
+                        }
+                        AtBq[i] += qprod(aws[i], bws);
+                    }
+                } else if (exact) {
                     for (int i = 0; i < 6; i++) {
                         for (int j = i; j < 6; j++) AtA[i * 6 + j] += (double)aw[i] * (double)aw[j];
                         AtB[i] += (double)aw[i] * (double)bw;
@@ -1043,6 +1084,12 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         if (!exact) {
             for (int i = 0; i < 36; i++) AtA[i] = AtAf[i];
             for (int i = 0; i < 6; i++) AtB[i] = AtBf[i];
+        }
+        if (quant) {
+            for (int i = 0; i < 6; i++) {
+                for (int j = i; j < 6; j++) AtA[i * 6 + j] = std::ldexp((double)AtAq[i * 6 + j], -(sexp[i] + sexp[j]));
+                AtB[i] = std::ldexp((double)AtBq[i], -(sexp[i] + sexp[6]));
+            }
         }
         for (int i = 0; i < 6; i++)
             for (int j = 0; j < i; j++) AtA[i * 6 + j] = AtA[j * 6 + i];
@@ -1076,19 +1123,29 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         for (int l = 0; l < NC; l++) { aver_res_label[l] = 0.f; num_pix_label[l] = 1; fix_label[l] = 0; }
         const float aver_res_old = aver_res;
         double rs_d = 0; float rs_f = 0.f;
+        /* EXACT: |res| <= |B| + sum_k |Var_k| |A_k| bounds the residuals; same power-of-two scaling as above */
+        int rexp = 0; int64_t rs_q = 0;
+        if (quant) {
+            float rb = colbound[6];
+            for (int c = 0; c < 6; c++) rb += std::fabs(Var[c]) * colbound[c];
+            rexp = scale_exponent(rb);
+        }
         for (size_t n = 0; n < N; n++) {
             const float ress_here = std::fabs(res[2 * n]) + std::fabs(res[2 * n + 1]);
             if (exact) fix_label[lab[n]] += fixq(ress_here, 30);
             else aver_res_label[lab[n]] += ress_here;
             num_pix_label[lab[n]]++;
-            if (exact) rs_d += (double)res[2 * n] * (double)res[2 * n] + (double)res[2 * n + 1] * (double)res[2 * n + 1];
+            if (quant) {
+                const float r0 = ldexpf(res[2 * n], rexp), r1 = ldexpf(res[2 * n + 1], rexp);
+                rs_q += qprod(r0, r0) + qprod(r1, r1);
+            } else if (exact) rs_d += (double)res[2 * n] * (double)res[2 * n] + (double)res[2 * n + 1] * (double)res[2 * n + 1];
             else { rs_f += res[2 * n] * res[2 * n]; rs_f += res[2 * n + 1] * res[2 * n + 1]; }
         }
         if (exact) {
             int64_t tot = 0;
             for (int l = 0; l < NC; l++) { tot += fix_label[l]; aver_res_label[l] = (float)fixval(fix_label[l], 30); }
             aver_res = (float)fixval(tot, 30) / float(2 * N);
-            res_sq = rs_d;
+            res_sq = quant ? std::ldexp((double)rs_q, -2 * rexp) : rs_d;
         } else {
             float tot = 0.f;
             for (int l = 0; l < NC; l++) tot += aver_res_label[l];
@@ -1188,7 +1245,7 @@ static void filterAndCompose(orc_ctx& c, float* twist) {
     for (int i = 0; i < 6; i++) c.twist_odometry[i] = (float)lg[i];
 }
 void orc_ctx::filterEstimateAndComputeT(float* twist) {
-    if (accum == ORC_ACCUM_EXACT) filterAndCompose<double>(*this, twist);
+    if (accum != ORC_ACCUM_F32) filterAndCompose<double>(*this, twist);
     else filterAndCompose<float>(*this, twist);
 }
 

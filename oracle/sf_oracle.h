@@ -32,7 +32,8 @@ extern "C" {
 
 /* accumulation policy for cross-pixel sums and the small dense algebra */
 #define ORC_ACCUM_F32 0   /* reference-literal: sequential float sums in the reference's traversal order, float algebra */
-#define ORC_ACCUM_EXACT 1 /* order-independent fixed-point / double sums, double algebra (what the CUDA path implements) */
+#define ORC_ACCUM_EXACT 1 /* every cross-pixel sum is an order-independent integer sum, double algebra: the CUDA path's contract */
+#define ORC_ACCUM_F64 2   /* like EXACT but plain double sums for the normal equations / |res|^2: measures EXACT's quantisation */
 
 typedef struct {
     int rows, cols;          /* finest level (StaticFusion.h:116) */

@@ -170,8 +170,6 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.lin, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.vlabel, a.P0 * F);
-    ok = ok && alloc((void**)&a.part1, sizeof(double) * 32 * a.max_blocks * F);
-    ok = ok && alloc((void**)&a.part2, sizeof(double) * a.max_blocks * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
     ok = ok && alloc((void**)&a.b_perpixel, sizeof(float) * a.P0 * F);
@@ -201,7 +199,7 @@ void sf_destroy(sf_ctx* c) {
     Arena& a = c->a;
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.lin);
-    cudaFree(a.vlabel); cudaFree(a.part1); cudaFree(a.part2); cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
+    cudaFree(a.vlabel); cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
     cudaFree(a.trace);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -28,6 +28,11 @@ constexpr int FIX_WARP_I = 22;  // warp intensity accumulator, packed with the 2
 constexpr int FIX_PRIOR = 32;   // seg prior sum (SegmentationBackground.cpp:75)
 constexpr int FIX_ABSB = 32;    // sum w|dt| for the initial mean residual (FrontEnd.cpp:590)
 constexpr int FIX_RES = 30;     // per-label residual sums (FrontEnd.cpp:661)
+// normal equations and |res|^2: columns scaled by powers of two below 2^QSCALE_BITS, products rounded to
+// integers with the 1.5*2^23 trick and summed as integers (associative -> any reduction order, bit-reproducible)
+constexpr int QSCALE_BITS = 10;
+constexpr float QMAGIC = 12582912.f;          // 1.5 * 2^23
+constexpr unsigned QMAGIC_BITS = 0x4B400000u;  // bit pattern of QMAGIC
 
 // geometry of one pyramid level (host computes the float constants exactly as the reference does)
 struct LevelGeom {
@@ -75,6 +80,12 @@ struct PairCtl {
     long long lab_fix[NC];
     int lab_cnt[NC];
     float inv_max_c, inv_max_d, aver_res, aver_res_old;
+    unsigned colmax_c[7], colmax_d[7];  // max |row entry| per column (6 Jacobian columns + rhs) with raw weights, float bits
+    float colbound[7];                  // bound of the normalised columns
+    int sexp[7];                        // power-of-two column scales
+    int rexp;                           // power-of-two scale of the residuals
+    long long acc_ne[27];               // integer normal equations: 21 upper-triangular AtA terms + 6 AtB terms
+    long long acc_rs;                   // integer |res|^2
     // ---- control ----
     int active;        // this pair takes part in the current step
     int irls_done;     // IRLS loop of the current step has exited
@@ -89,6 +100,15 @@ struct PairCtl {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long fixq(float x, int s) { return __float2ll_rn(ldexpf(x, s)); }
 __device__ __forceinline__ double fixval(long long acc, int s) { return ldexp((double)acc, -s); }
+__host__ __device__ __forceinline__ int scale_exponent(float bound) {
+    if (!(bound > 0.f) || !isfinite(bound)) return 0;
+    int e;
+    (void)frexpf(bound, &e);  // bound = m * 2^e, m in [0.5, 1)
+    int s = QSCALE_BITS - e;
+    if (s > 100) s = 100;
+    if (s < -100) s = -100;
+    return s;
+}
 
 // ---------------------------------------------------------------------------------------------
 // small dense algebra in double — same operation sequences as the oracle's templates

@@ -30,8 +30,6 @@ struct Arena {
     float* warp_i;              // [F][P0]
     float* lin;                 // [F][NPLANES][P0]
     uint8_t* vlabel;            // [F][P0]
-    double* part1;              // [F][max_blocks][32]
-    double* part2;              // [F][max_blocks]
     PairCtl* ctl;               // [F]
     PairOut* out;               // [F]
     float* b_perpixel;          // [F][P0]

@@ -1,0 +1,99 @@
+"""Frame sharding over GPUs: one process per GPU, contiguous blocks of frame pairs per rank.
+
+The reference is strictly sequential frame-to-model SLAM; what shards is its frame-to-frame form
+(prediction := previous raw frame, ``StaticFusion-datasets.cpp:109-144``) where pair (t-1, t) is an
+independent solve.  There is no data-path collective: each rank solves its own pairs and ONE
+all-gather of the small per-pair result rows (pose, twist, b_segm, counters; 48 floats) follows the
+whole batch.  The global trajectory is the prefix product of the gathered increments
+(``cam_pose = cam_pose + pose_aux``, ``FrontEnd.cpp:1134-1137``), done on the host in float64.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ROW = 16 + 6 + 24 + 2  # T (column-major 4x4), twist_old, b_segm, irls_iters, status
+
+
+def shard_pairs(n_pairs: int, rank: int, world: int) -> tuple[int, int]:
+    """[start, stop) of the pairs rank `rank` solves: contiguous blocks, remainder spread over the first ranks."""
+    base, rem = divmod(n_pairs, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """[first, last] inclusive frames rank `rank` needs for its pairs of a sequence (one halo frame)."""
+    s, e = shard_pairs(n_frames - 1, rank, world)
+    return s, e  # pairs s..e-1 use frames s..e
+
+
+def pack_rows(result) -> np.ndarray:
+    n = result.T.shape[0]
+    rows = np.zeros((n, ROW), np.float32)
+    rows[:, 0:16] = result.T
+    rows[:, 16:22] = result.twist_old
+    rows[:, 22:46] = result.b_segm
+    rows[:, 46] = result.irls_iters
+    rows[:, 47] = result.status
+    return rows
+
+
+def unpack_rows(rows: np.ndarray) -> dict:
+    return dict(T=rows[:, 0:16].copy(), twist_old=rows[:, 16:22].copy(), b_segm=rows[:, 22:46].copy(),
+                irls_iters=rows[:, 46].astype(np.int32), status=rows[:, 47].astype(np.int32))
+
+
+def gather_rows(local_rows: np.ndarray, n_pairs: int, device=None) -> np.ndarray:
+    """All-gather the per-pair rows of every rank into the global (n_pairs, ROW) table (same on all ranks).
+
+    Uses the initialised ``torch.distributed`` group: NCCL when `device` is a CUDA device (the rows are
+    staged through a device tensor), gloo on CPU.  Single process / no group: returns the input.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        assert local_rows.shape[0] == n_pairs
+        return local_rows
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [shard_pairs(n_pairs, r, world) for r in range(world)]
+    cap = max(e - s for s, e in counts)
+    buf = torch.zeros((cap, ROW), dtype=torch.float32, device=device if device is not None else "cpu")
+    s, e = counts[rank]
+    assert local_rows.shape[0] == e - s
+    if e > s:
+        buf[: e - s] = torch.from_numpy(np.ascontiguousarray(local_rows)).to(buf.device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    table = np.zeros((n_pairs, ROW), np.float32)
+    for r, (rs, re) in enumerate(counts):
+        if re > rs:
+            table[rs:re] = out[r][: re - rs].cpu().numpy()
+    return table
+
+
+def compose_trajectory(T_colmajor: np.ndarray, start: np.ndarray | None = None) -> np.ndarray:
+    """Prefix product of the increments: pose_k = pose_{k-1} @ T_k (float64), shape (n+1, 4, 4)."""
+    n = T_colmajor.shape[0]
+    poses = np.zeros((n + 1, 4, 4), np.float64)
+    poses[0] = np.eye(4) if start is None else start
+    for k in range(n):
+        poses[k + 1] = poses[k] @ T_colmajor[k].reshape(4, 4).T.astype(np.float64)
+    return poses
+
+
+def solve_sequence_sharded(solver, depth, inten, device=None, want_images=False):
+    """Solve the pairs of a frame sequence owned by this rank and gather every rank's result rows.
+
+    `depth` / `inten` hold the WHOLE sequence (n_frames, rows, cols) on every rank (synthetic data is
+    generated locally); only the rank's frame block is uploaded.  Returns (global table dict, local BatchResult).
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    n_frames = int(depth.shape[0])
+    f0, f1 = shard_frames(n_frames, rank, world)
+    local = solver.solve_sequence(depth[f0:f1 + 1], inten[f0:f1 + 1], want_images=want_images)
+    table = gather_rows(pack_rows(local), n_frames - 1, device=device)
+    return unpack_rows(table), local

@@ -67,6 +67,8 @@ def _rot(rx: float, ry: float, rz: float) -> np.ndarray:
 
 def camera_pose(scene: Scene, t: int) -> np.ndarray:
     """World-from-camera 4x4 (float64) at frame t.  Camera axes: x right, y down, z forward."""
+    if isinstance(scene, str):
+        scene = SCENES[scene]
     w = 2.0 * math.pi / 90.0  # 3 s period at 30 Hz
     ax, ay, az = scene.trans_amp
     dx, dy, dz = scene.trans_per_frame

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): integer / index outputs (cluster labels, connectivity, static mask,
+iteration counts) bit-exact; pose within 1e-5 m and 1e-5 rad per pair.  Because every cross-pixel sum of
+the CUDA path is an order-independent integer sum and the per-pixel float expressions keep
+the reference's operation order, the CUDA path is in fact BIT-IDENTICAL to the oracle's EXACT policy; the
+tests assert the stated tolerance first and bit-equality second, so a future 1-ulp libm difference shows
+up as the second assertion, not as a silent drift.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from common import frames, oracle_params_from, pose_error
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-5    # north_star: <= 1e-5 m per frame
+POSE_TOL_RAD = 1e-5  # north_star: <= 1e-5 rad per frame
+
+
+@pytest.fixture(scope="module")
+def gpu(sf_mod):
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return sf_mod
+
+
+def run_oracle(O, p, dc, ic, dp, ip, twist_old=None, stop_step=-1):
+    o = O.Oracle(oracle_params_from(O, p), O.ACCUM_EXACT)
+    o.solve_pair(dc, ic, dp, ip, twist_old=twist_old, stop_step=stop_step)
+    return o
+
+
+def test_library_is_the_native_cuda_build(gpu):
+    assert os.path.exists(gpu.LIB_PATH)
+    s = gpu.StaticFusionSolver(gpu.default_params(240, 320), max_batch=1)
+    assert s.stream != 0
+    s.close()
+
+
+@pytest.mark.parametrize("res,scene", [((240, 320), "dynamic"), ((480, 640), "dynamic"), ((240, 320), "fr1_360")])
+def test_pyramids_and_clustering_bit_exact(gpu, oracle_mod, res, scene):
+    rows, cols = res
+    d, c = frames(scene, 3, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=2, trace=True)
+    s.solve_sequence(d, c)
+    for k in range(2):
+        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k])
+        for L in range(p.ctf_levels):
+            for name in ("depth", "intensity", "depth_pred", "intensity_pred"):
+                assert np.array_equal(s.debug_plane(name, k, L), o.image(name, L)), (name, L)
+            assert np.array_equal(s.debug_labels(k, L), o.labels(L)), ("labels", L)
+        cen, conn = s.debug_kmeans(k)
+        assert np.array_equal(cen, o.kmeans_centres())
+        assert np.array_equal(conn, o.connectivity())
+    s.close()
+
+
+def test_first_step_linearisation_bit_exact(gpu, oracle_mod):
+    """calculateCoord / calculateDerivatives / computeWeights at the coarsest level, before any cross-pixel sum."""
+    rows, cols = 240, 320
+    d, c = frames("dynamic", 2, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=1, trace=True)
+    s.debug_set_stop_step(0)
+    s.solve_sequence(d, c)
+    o = run_oracle(oracle_mod, p, d[1], c[1], d[0], c[0], stop_step=0)
+    L = p.ctf_levels - 1
+    null = o.image("null", L) > 0
+    interior = np.zeros_like(null)
+    interior[1:-1, 1:-1] = True
+    valid = ~null & interior
+    assert np.array_equal(s.debug_plane("valid", 0, L) > 0, valid)
+    for name in ("depth_inter", "xx_inter", "yy_inter", "dcu", "dcv", "ddu", "ddv", "weights_c", "weights_d"):
+        assert np.array_equal(s.debug_plane(name, 0, L)[valid], o.image(name, L)[valid]), name
+    for name in ("dct", "ddt"):
+        assert np.array_equal(s.debug_plane(name, 0, L), o.image(name, L)), name
+    tg, to = s.debug_trace(0)[0], o.trace()[0]
+    assert np.array_equal(tg[8:56], to[8:56])  # b_prior, lambda_t_w
+    s.close()
+
+
+def test_warp_and_second_level_linearisation(gpu, oracle_mod):
+    """After one pose update the warp input T differs by ~1e-9 from the oracle's: images agree to float rounding."""
+    rows, cols = 240, 320
+    d, c = frames("dynamic", 2, rows, cols)
+    p = gpu.default_params(rows, cols)
+    step = p.max_iter_per_level  # (level 1, k 0)
+    s = gpu.StaticFusionSolver(p, max_batch=1, trace=True)
+    s.debug_set_stop_step(step)
+    s.solve_sequence(d, c)
+    o = run_oracle(oracle_mod, p, d[1], c[1], d[0], c[0], stop_step=step)
+    L = p.ctf_levels - 2
+    for name, tol in (("depth_warped", 2e-6), ("intensity_warped", 2e-6)):
+        g, r = s.debug_plane(name, 0, L), o.image(name, L)
+        assert np.array_equal(g == 0, r == 0), name
+        assert np.abs(g - r).max() < tol, name
+        assert np.array_equal(g, r), name
+    null = o.image("null", L) > 0
+    interior = np.zeros_like(null)
+    interior[1:-1, 1:-1] = True
+    valid = ~null & interior
+    assert np.array_equal(s.debug_plane("valid", 0, L) > 0, valid)
+    for name, tol in (("depth_inter", 2e-6), ("dcu", 1e-4), ("ddu", 1e-4), ("weights_c", 1e-4)):
+        assert np.abs(s.debug_plane(name, 0, L)[valid] - o.image(name, L)[valid]).max() < tol, name
+    for name in ("depth_inter", "xx_inter", "yy_inter", "dcu", "dcv", "ddu", "ddv", "weights_c", "weights_d"):
+        assert np.array_equal(s.debug_plane(name, 0, L)[valid], o.image(name, L)[valid]), name
+    s.close()
+
+
+def test_irls_trace_matches_oracle(gpu, oracle_mod):
+    """Per IRLS iteration: Var, b_segm, mean residual; per step: valid-pixel and iteration counts."""
+    rows, cols = 240, 320
+    d, c = frames("dynamic", 4, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=3, trace=True)
+    r = s.solve_sequence(d, c)
+    H, I = gpu.TRACE_HDR, gpu.TRACE_IRLS
+    for k in range(3):
+        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k])
+        tg, to = s.debug_trace(k), o.trace()
+        assert np.array_equal(tg[:, 0], to[:, 0])          # same steps executed (outer-loop exits agree)
+        assert r.irls_iters[k] == o.total_irls()
+        for st in np.nonzero(to[:, 0])[0]:
+            assert tg[st, 3] == to[st, 3] and tg[st, 4] == to[st, 4]  # N valid, IRLS iterations
+            n = int(to[st, 4])
+            ig, io = tg[st, H:H + I * n].reshape(n, I), to[st, H:H + I * n].reshape(n, I)
+            assert np.abs(ig[:, :6] - io[:, :6]).max() < 2e-6      # Var
+            assert np.abs(ig[:, 6:30] - io[:, 6:30]).max() < 1e-3  # b_segm
+            assert np.allclose(ig[:, 30], io[:, 30], rtol=1e-4)    # mean residual
+            assert np.abs(tg[st, 56:62] - to[st, 56:62]).max() < 2e-6   # filtered level twist
+            assert np.abs(tg[st, 62:78] - to[st, 62:78]).max() < 2e-6   # T_odometry after the step
+        assert np.array_equal(tg, to)  # bit-identical trace: Var, b_segm, residual norms, maxima, poses
+    s.close()
+
+
+@pytest.mark.parametrize("scene,n", [("fr1_360", 12), ("dynamic", 8), ("walking_xyz", 8)])
+def test_pose_and_segmentation_parity(gpu, oracle_mod, scene, n):
+    """north_star bar: pose <= 1e-5 m / 1e-5 rad per pair; labels and static mask bit-exact; equal iteration counts."""
+    rows, cols = 240, 320
+    d, c = frames(scene, n + 1, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=n)
+    r = s.solve_sequence(d, c)
+    Tg = r.T_matrices()
+    worst = (0.0, 0.0)
+    for k in range(n):
+        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k])
+        dt, dr = pose_error(Tg[k], o.T())
+        worst = (max(worst[0], dt), max(worst[1], dr))
+        assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD, (k, dt, dr)
+        assert r.irls_iters[k] == o.total_irls() and r.status[k] == o.status()
+        assert np.array_equal(r.labels[k].astype(np.int32), o.labels(0))
+        assert np.array_equal(r.b_perpixel[k] > 0.5, o.b_perpixel() > 0.5)
+        assert np.abs(r.b_segm[k] - o.b_segm()).max() < 1e-3
+        assert np.abs(r.twist_old[k] - o.twists()[1]).max() < 1e-5
+        # bit-identity (see module docstring)
+        assert np.array_equal(Tg[k], o.T()) and np.array_equal(r.b_segm[k], o.b_segm())
+        assert np.array_equal(r.b_perpixel[k], o.b_perpixel()) and np.array_equal(r.twist_old[k], o.twists()[1])
+    print(f"{scene}: worst pose error {worst[0]:.2e} m {worst[1]:.2e} rad over {n} pairs")
+    s.close()
+
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[14:-4] for p in GOLD])
+def test_against_committed_golden_vectors(gpu, oracle_mod, path):
+    g = np.load(path)
+    kw = {}
+    for (name, ctype), v in zip(oracle_mod.Params._fields_, g["params"]):
+        kw[name] = int(v) if ctype is oracle_mod.C.c_int else float(v)
+    p = gpu.default_params(kw.pop("rows"), kw.pop("cols"), **kw)
+    d = (g["depth_mm"].astype(np.float64) * (1.0 / 1000.0)).astype(np.float32)
+    c = g["intensity"]
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r = s.solve_batch(d[1:2], c[1:2], d[0:1], c[0:1])
+    dt, dr = pose_error(r.T_matrices()[0], g["T"])
+    assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+    assert np.array_equal(r.labels[0], g["labels"])
+    assert np.array_equal(r.b_perpixel[0] > 0.5, g["mask"])
+    assert r.irls_iters[0] == int(g["irls"]) and r.status[0] == int(g["status"])
+    s.close()
+
+
+def test_config1_single_level_gauss_newton(gpu, oracle_mod):
+    """BASELINE config 1: 1 level, 5 relinearisations x 1 IRLS iteration, no segmentation."""
+    rows, cols = 240, 320
+    d, c = frames("static_yaw", 2, rows, cols)
+    p = gpu.default_params(rows, cols, ctf_levels=1, max_iter_per_level=5, max_iter_irls=1, enable_segmentation=0,
+                           use_motion_filter=0, outer_exit_threshold=0.0)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r = s.solve_sequence(d, c)
+    o = run_oracle(oracle_mod, p, d[1], c[1], d[0], c[0])
+    dt, dr = pose_error(r.T_matrices()[0], o.T())
+    assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+    assert r.irls_iters[0] == 5 == o.total_irls()
+    assert np.all(r.b_perpixel[0] == 1.0) and np.all(r.labels[0] == 0)
+    s.close()
+
+
+def test_config3_vga_four_levels(gpu, oracle_mod):
+    rows, cols = 480, 640
+    d, c = frames("dynamic", 3, rows, cols)
+    p = gpu.default_params(rows, cols, ctf_levels=4)
+    s = gpu.StaticFusionSolver(p, max_batch=2)
+    r = s.solve_sequence(d, c)
+    for k in range(2):
+        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k])
+        dt, dr = pose_error(r.T_matrices()[k], o.T())
+        assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+        assert np.array_equal(r.labels[k].astype(np.int32), o.labels(0))
+        assert np.array_equal(r.b_perpixel[k] > 0.5, o.b_perpixel() > 0.5)
+        assert r.irls_iters[k] == o.total_irls()
+    s.close()
+
+
+def test_motion_filter_state_is_threaded_through(gpu, oracle_mod):
+    """twist_odometry_old in/out (FrontEnd.cpp:733,1143-1144): chaining two pairs matches the oracle doing the same."""
+    rows, cols = 240, 320
+    d, c = frames("fr1_360", 3, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r1 = s.solve_batch(d[1:2], c[1:2], d[0:1], c[0:1])
+    r2 = s.solve_batch(d[2:3], c[2:3], d[1:2], c[1:2], twist_old=r1.twist_old)
+    o1 = run_oracle(oracle_mod, p, d[1], c[1], d[0], c[0])
+    o2 = run_oracle(oracle_mod, p, d[2], c[2], d[1], c[1], twist_old=o1.twists()[1])
+    dt, dr = pose_error(r2.T_matrices()[0], o2.T())
+    assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD
+    r2z = s.solve_batch(d[2:3], c[2:3], d[1:2], c[1:2])
+    assert not np.array_equal(r2.T, r2z.T)  # the state really is used
+    s.close()
+
+
+def test_degenerate_inputs(gpu):
+    """empty / identical inputs return identity and a status bit instead of the reference's NaN."""
+    rows, cols = 240, 320
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=2)
+    z = np.zeros((2, rows, cols), np.float32)
+    d, c = frames("static_small", 1, rows, cols)
+    dc = np.stack([z[0], d[0]])
+    ic = np.stack([z[0], c[0]])
+    r = s.solve_batch(dc, ic, dc, ic)
+    assert r.status[0] & gpu.STATUS_NO_VALID_PIXELS
+    assert np.array_equal(r.T_matrices()[0], np.eye(4, dtype=np.float32))
+    assert np.all(r.b_perpixel[0] == 1.0) and np.all(r.labels[0] == 24)
+    assert r.status[1] & gpu.STATUS_ZERO_RESIDUAL
+    assert np.allclose(r.T_matrices()[1], np.eye(4), atol=1e-7)
+    assert np.all(np.isfinite(r.T)) and np.all(np.isfinite(r.b_segm))
+    s.close()
