@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the StaticFusion joint odometry + segmentation solver on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5]
+
+One "step" = one pass of the hot path (createImagePyramid(true) + runSolver(true) + buildSegmImage(),
+reference StaticFusion-datasets.cpp:171-180) over one batch of synthetic frame pairs.
+
+* metric  (BASELINE.json): QVGA solver iterations / s.  One iteration = one pass of the IRLS loop body
+  (FrontEnd.cpp:611-684) at the finest level of the config; iterations at coarser levels are counted as
+  finest-level equivalents by their valid-pixel ratio.  frames/s is reported alongside.
+* value   : inputs already resident in HBM, device-timed (CUDA events on the library's stream, max over ranks).
+* e2e     : the same batch through the public API with pinned HOST buffers: H2D of the frames, solve,
+            D2H of poses + per-pixel static weights + labels, all inside the timed region.
+* roofline: the dominant kernel (irls_pass1 at the finest level), algorithmic bytes (48 B per valid pixel
+            per pass = half of SURVEY §8d's 96*N per iteration) over its CUDA-event time, against the
+            measured HBM peak in MEASURED_PEAKS.json.
+* cpu_baseline / --impl reference: the CPU oracle (a port: the reference itself cannot be built here)
+  timed on the box's host cores on a bounded sample of the same workload.
+
+N > 1: launched by torchrun, one rank per GPU, frame pairs sharded (no data-path collective), one NCCL
+all-gather of the 48-float result rows per batch; weak scaling (per-GPU batch fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # id: (workload name, rows, cols, ctf_levels, pairs per GPU, scene)
+    2: ("config2: QVGA 320x240, 3-level pyramid, full IRLS + segmentation alternation", 240, 320, 3, 512, "dynamic"),
+    3: ("config3: VGA 640x480, 4-level pyramid, full solver", 480, 640, 4, 256, "dynamic"),
+    4: ("config4: fr3/walking_xyz-shaped QVGA sequence, reference default 5 levels", 240, 320, 5, 125, "walking_xyz"),
+    5: ("config5: stress 1280x960, 4-level pyramid", 960, 1280, 4, 64, "dynamic"),
+}
+
+
+def _render(args):
+    from staticfusion_b200 import synth
+    scene, t, rows, cols = args
+    return synth.render_frame(scene, t, rows, cols)
+
+
+def make_frames(scene, n, rows, cols, start=0):
+    """Render n frames on the host cores (seeded, deterministic)."""
+    nproc = max(1, min(os.cpu_count() or 1, 16))
+    jobs = [(scene, start + i, rows, cols) for i in range(n)]
+    if nproc > 1 and n > 4:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            out = pool.map(_render, jobs, chunksize=max(1, n // (4 * nproc)))
+    else:
+        out = [_render(j) for j in jobs]
+    return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def pair_indices(n_pairs, n_distinct):
+    """pair k -> (prediction frame, current frame) cycling through the distinct rendered frames."""
+    k = np.arange(n_pairs) % (n_distinct - 1)
+    return k, k + 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def l0_equiv_iterations(n_valid, iters):
+    """Finest-level-equivalent IRLS iterations of a batch: sum_steps it * N / N_finest, per pair."""
+    n_valid = n_valid.astype(np.float64)
+    iters = iters.astype(np.float64)
+    executed = n_valid > 0
+    last = np.where(executed.any(axis=1), executed.shape[1] - 1 - np.argmax(executed[:, ::-1], axis=1), 0)
+    n_fine = n_valid[np.arange(n_valid.shape[0]), last]
+    work = (n_valid * iters).sum(axis=1)
+    return float(np.where(n_fine > 0, work / np.maximum(n_fine, 1), 0).sum()), float(work.sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(rows, cols, levels):
+    from oracle import oracle as O
+    _W["O"] = O
+    _W["o"] = O.Oracle(O.driver_params(rows, cols, ctf_levels=levels), O.ACCUM_F32)  # reference-literal float sums
+
+
+def _cpu_solve(job):
+    dc, ic, dp, ip = job
+    O, o = _W["O"], _W["o"]
+    o.solve_pair(dc, ic, dp, ip)
+    tr = o.trace()
+    return tr[:, 3].astype(np.int64), tr[:, 4].astype(np.int64)
+
+
+def cpu_run(d, c, pidx, cidx, rows, cols, levels, nproc):
+    """Solve the listed pairs with nproc oracle processes; returns (seconds, finest-equivalent iterations, pairs)."""
+    jobs = [(d[j], c[j], d[i], c[i]) for i, j in zip(pidx, cidx)]
+    if nproc == 1:
+        _cpu_init(rows, cols, levels)
+        t0 = time.perf_counter()
+        res = [_cpu_solve(j) for j in jobs]
+        dt = time.perf_counter() - t0
+    else:
+        with mp.get_context("fork").Pool(nproc, initializer=_cpu_init, initargs=(rows, cols, levels)) as pool:
+            pool.map(_cpu_solve, jobs[:nproc])  # warm the workers (page-in, allocation)
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_solve, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+    nv = np.stack([r[0] for r in res])
+    it = np.stack([r[1] for r in res])
+    eq, _ = l0_equiv_iterations(nv, it)
+    return dt, eq, len(jobs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the config's)")
+    ap.add_argument("--distinct", type=int, default=65, help="distinct rendered frames cycled through the batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name, rows, cols, levels, F, scene = CONFIGS[a.config]
+    if a.batch:
+        F = a.batch
+    n_distinct = max(2, min(a.distinct, F + 1))
+    metric = "solver_iterations_per_s"
+    unit = "finest-level-equivalent IRLS iterations/s"
+    cfg = {"workload": name, "resolution": f"{cols}x{rows}", "ctf_levels": levels, "pairs_per_gpu": F, "scene": scene,
+           "distinct_frames": n_distinct, "params": "reference drivers (StaticFusion-datasets.cpp:79-94)",
+           "l2_policy": "working set per step >> 126 MB L2 (inputs larger than L2)", "parallelism": f"frame-sharded x{world}"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        nproc = os.cpu_count() or 1
+        d, c = make_frames(scene, n_distinct, rows, cols)
+        per_step = max(nproc, min(4 * nproc, 64))
+        pidx, cidx = pair_indices(per_step, n_distinct)
+        for _ in range(min(a.warmup, 1)):
+            cpu_run(d, c, pidx[:nproc], cidx[:nproc], rows, cols, levels, nproc)
+        tot_t = tot_eq = tot_pairs = 0.0
+        for _ in range(a.steps):
+            dt, eq, n = cpu_run(d, c, pidx, cidx, rows, cols, levels, nproc)
+            tot_t += dt; tot_eq += eq; tot_pairs += n
+        v = tot_eq / tot_t
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "frames_per_s": tot_pairs / tot_t,
+                "cpu_baseline": {"value": v, "unit": unit, "cores": nproc, "kind": "port",
+                                 "sample": f"{per_step} pairs per step x {a.steps} steps of the workload, one oracle process per core "
+                                           "(reference-literal float accumulation; the reference itself cannot be built here)"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+
+    import staticfusion_b200 as sf
+    from staticfusion_b200 import sharding
+    from staticfusion_b200.solver import BatchResult
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    d, c = make_frames(scene, n_distinct, rows, cols, start=97 * rank)
+    pidx, cidx = pair_indices(F, n_distinct)
+    # host (pinned) and device copies of the batch
+    h = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (d[cidx], c[cidx], d[pidx], c[pidx])]
+    g = [x.to(dev) for x in h]
+    p = sf.default_params(rows, cols, ctf_levels=levels)
+    s = sf.StaticFusionSolver(p, device=local_rank, max_batch=F)
+    stream = torch.cuda.ExternalStream(s.stream, device=dev)
+    out = BatchResult(F, rows, cols, True, pinned=True)
+
+    def device_step():
+        s.upload_pairs(*g)  # device-to-device: frames land in the pyramids' level-0 slots
+        s.launch()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        device_step()
+    s.sync()
+    # --- timed region: EXACTLY K steps, device-timed on the library's stream, per-kernel events on
+    s.profile_enable(True)
+    device_step(); s.sync()  # one profiled warm step so the event pool exists
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_ms = np.zeros((sf._lib.PROF_CLASSES, sf._lib.PROF_LEVELS))
+    prof_n = np.zeros_like(prof_ms)
+    launches = 0
+    t_host0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(a.steps):
+        device_step()
+        if world > 1:  # one all-gather of the small result rows per batch
+            r_local = s.download(want_images=False)
+            sharding.gather_rows(sharding.pack_rows(r_local), F * world, device=dev)
+        launches += s.last_launch_count
+        ms, cnt = s.profile_read()  # waits for the step; events only, no extra kernels
+        prof_ms += ms; prof_n += cnt
+    e1.record(stream)
+    barrier()
+    t_host = time.perf_counter() - t_host0
+    clk = clocks.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    s.profile_enable(False)
+    res = s.download(want_images=False)
+    nv, it = s.step_stats()
+    eq_iters, irls_px = l0_equiv_iterations(nv, it)
+
+    # --- e2e: public API, pinned host buffers in, results out, every step
+    hn = [x.numpy() for x in h]
+    for _ in range(2):
+        s.solve_batch(*hn, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        s.solve_batch(*hn, out=out)
+        if world > 1:
+            sharding.gather_rows(sharding.pack_rows(out), F * world, device=dev)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s, eq_iters, irls_px], dtype=torch.float64, device=dev)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_s = float(tmax[0]), float(tmax[1])
+        eq_total, px_total = float(tsum[2]), float(tsum[3])
+    else:
+        eq_total, px_total = eq_iters, irls_px
+
+    if rank == 0:
+        sec = elapsed_ms / 1e3
+        value = eq_total * a.steps / sec
+        fps = F * world * a.steps / sec
+        # roofline of the dominant kernel: irls_pass1 at the finest level (class 5, level 0), rank 0
+        fine = nv.shape[1] - 1 - np.argmax((nv > 0)[:, ::-1], axis=1)
+        steps_fine = [st for st in range(nv.shape[1]) if st // p.max_iter_per_level == levels - 1]
+        bytes_pass1 = 48.0 * float(sum((nv[:, st] * it[:, st]).sum() for st in steps_fine)) * a.steps
+        ms_pass1 = float(prof_ms[5, 0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_pass1 / (ms_pass1 * 1e-3) / 1e9 if ms_pass1 > 0 else 0.0
+        n_l0_launches = int(prof_n[5, 0])
+        roof = {"bound": "hbm", "kernel": "irls_pass1_kernel (finest level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": bytes_pass1 / max(n_l0_launches, 1), "launches": n_l0_launches,
+                "avg_launch_ms": ms_pass1 / max(n_l0_launches, 1)}
+        names = sf._lib.PROF_NAMES
+        kern = {f"{names[k]}_L{l}": round(float(prof_ms[k, l]) / a.steps, 4) for k in range(prof_ms.shape[0]) for l in range(prof_ms.shape[1])
+                if prof_n[k, l] > 0}
+        # whole-step algorithmic traffic: 96 B per valid pixel per IRLS iteration + 61 B/px linearise + 40 B/px warp
+        step_bytes = 96.0 * px_total / world
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "frames_per_s": fps,
+                "irls_iterations_per_pair": float(res.irls_iters.mean()), "status_nonzero_pairs": int((res.status != 0).sum()),
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": eq_total * a.steps / e2e_s, "unit": unit, "frames_per_s": F * world * a.steps / e2e_s,
+                        "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)),
+                        "d2h_bytes_per_step": int(F * (rows * cols * 5 + 200)), "timing": "host wall clock around the public call"},
+                "roofline": roof, "kernel_ms_per_step": kern,
+                "irls_algorithmic_gbs_whole_step": step_bytes / (elapsed_ms / a.steps * 1e-3) / 1e9,
+                "host_wall_ms_per_step": 1e3 * t_host / a.steps}
+        if not a.no_cpu_baseline:
+            # bounded single-thread sample (the reference is single-threaded): ~10 s of CPU work
+            dt, eq, n = cpu_run(d, c, pidx[:4], cidx[:4], rows, cols, levels, 1)
+            n_s = int(min(max(16, 10.0 / (dt / n)), F))
+            dt, eq, n = cpu_run(d, c, pidx[:n_s], cidx[:n_s], rows, cols, levels, 1)
+            line["cpu_baseline"] = {"value": eq / dt, "unit": unit, "cores": 1, "kind": "port", "frames_per_s": n / dt,
+                                    "sample": f"first {n} pairs of the batch, single thread, reference-literal float accumulation "
+                                              f"({dt:.1f} s); the reference itself cannot be built here"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -172,6 +172,18 @@ uint64_t sf_stream(sf_ctx* ctx);
 /* Number of kernel launches enqueued by the last sf_launch. */
 int sf_last_launch_count(sf_ctx* ctx);
 
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
+#define SF_PROF_CLASSES 9 /* 0 init, 1 pyramid, 2 clustering, 3 warp, 4 linearise, 5 irls_pass1, 6 irls_pass2, 7 pose_update, 8 finish */
+#define SF_PROF_LEVELS 8
+/* Record a CUDA-event pair around every kernel group of the following sf_launch calls (on the context's stream). */
+int sf_profile_enable(sf_ctx* ctx, int on);
+/* After sf_sync: summed device time [ms] and launch counts per (class, pyramid level) of the last sf_launch;
+ * both arrays hold SF_PROF_CLASSES*SF_PROF_LEVELS entries, index class*SF_PROF_LEVELS + image_level. */
+int sf_profile_read(sf_ctx* ctx, float* ms, int* launches);
+/* Per pair and step (ctf_levels*max_iter_per_level steps, index level*max_iter_per_level + k) of the last solve:
+ * valid pixels N (0 = step not executed) and IRLS iterations run.  Arrays hold n_pairs*steps ints. */
+int sf_get_step_stats(sf_ctx* ctx, int* n_valid, int* irls_iters);
+
 /* ---- introspection for parity tests ------------------------------------------------------------ */
 /* Halt the next solves right after the linearisation of step (level*max_iter_per_level + k); -1 = run to the end. */
 int sf_debug_set_stop_step(sf_ctx* ctx, int stop_step);

@@ -29,7 +29,11 @@ EXPORTS = [
     "sf_solve_batch", "sf_solve_sequence", "sf_upload_pairs", "sf_upload_sequence", "sf_launch", "sf_sync",
     "sf_download", "sf_stream", "sf_last_launch_count", "sf_debug_set_stop_step", "sf_debug_get_plane",
     "sf_debug_get_labels", "sf_debug_get_kmeans", "sf_debug_get_trace", "sf_last_error", "sf_abi_version",
+    "sf_profile_enable", "sf_profile_read", "sf_get_step_stats",
 ]
+PROF_CLASSES = 9
+PROF_LEVELS = 8
+PROF_NAMES = ["init", "pyramid", "clustering", "warp", "linearise", "irls_pass1", "irls_pass2", "pose_update", "finish"]
 
 
 class SfParams(C.Structure):
@@ -104,6 +108,9 @@ def lib():
     L.sf_debug_get_labels.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.sf_debug_get_kmeans.argtypes = [vp, C.c_int, fp, u8p]
     L.sf_debug_get_trace.argtypes = [vp, C.c_int, fp, C.c_int]
+    L.sf_profile_enable.argtypes = [vp, C.c_int]
+    L.sf_profile_read.argtypes = [vp, fp, ip]
+    L.sf_get_step_stats.argtypes = [vp, ip, ip]
     L.sf_last_error.restype = C.c_char_p
     L.sf_abi_version.restype = C.c_int
     _lib = L

@@ -44,6 +44,35 @@ struct sf_ctx {
     bool have_cur = false, have_pred = false, trio_pyr_pred = false;
     float h_twist_old[6] = {0, 0, 0, 0, 0, 0};
     std::vector<PairOut> h_out;
+    std::vector<int> h_ci, h_pi;  // pair -> frame tables staged for async upload (must outlive the copy)
+    // profiling: one event pair per kernel group of the last launch
+    bool prof_on = false;
+    struct ProfRec { int cls, level; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+static cudaEvent_t prof_event(sf_ctx* c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+struct ProfScope {
+    sf_ctx* c;
+    bool on;
+    cudaEvent_t e1;
+    ProfScope(sf_ctx* ctx, int cls, int level) : c(ctx), on(ctx->prof_on), e1(nullptr) {
+        if (!on) return;
+        cudaEvent_t e0 = prof_event(c);
+        e1 = prof_event(c);
+        cudaEventRecord(e0, c->stream);
+        c->prof.push_back({cls, level, e0, e1});
+    }
+    ~ProfScope() { if (on) cudaEventRecord(e1, c->stream); }
 };
 
 static void fill_dev_params(sf_ctx* c) {
@@ -173,6 +202,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
     ok = ok && alloc((void**)&a.b_perpixel, sizeof(float) * a.P0 * F);
+    ok = ok && alloc((void**)&a.stepstat, sizeof(int) * 2 * a.trace_steps * F);
     if (ok && (flags & 1)) ok = alloc((void**)&a.trace, sizeof(float) * SF_TRACE_STEP * a.trace_steps * F);
     if (!ok) {
         const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -200,7 +230,8 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.lin);
     cudaFree(a.vlabel); cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
-    cudaFree(a.trace);
+    cudaFree(a.trace); cudaFree(a.stepstat);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -247,12 +278,16 @@ int sf_upload_pairs(sf_ctx* c, int n_pairs, const float* depth_cur, const float*
     if ((rc = upload_stack(c, c->a.pyr_i, 0, 2, n_pairs, inten_cur, in_space))) return rc;
     if ((rc = upload_stack(c, c->a.pyr_d, 1, 2, n_pairs, depth_pred, in_space))) return rc;
     if ((rc = upload_stack(c, c->a.pyr_i, 1, 2, n_pairs, inten_pred, in_space))) return rc;
-    std::vector<int> ci(n_pairs), pi(n_pairs);
-    for (int k = 0; k < n_pairs; k++) { ci[k] = 2 * k; pi[k] = 2 * k + 1; }
+    std::vector<int>&ci = c->h_ci, &pi = c->h_pi;
+    if ((int)ci.size() != n_pairs || ci[0] != 0 || pi[0] != 1) {
+        CU(cudaStreamSynchronize(c->stream));  // a previous async copy may still read the tables
+        ci.resize(n_pairs); pi.resize(n_pairs);
+        for (int k = 0; k < n_pairs; k++) { ci[k] = 2 * k; pi[k] = 2 * k + 1; }
+    }
     CU(cudaMemcpyAsync(c->d_cur_idx, ci.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
-    CU(cudaStreamSynchronize(c->stream));  // ci/pi are stack-lifetime host buffers
+    if (twist_old_in) CU(cudaStreamSynchronize(c->stream));  // caller may free twist_old_in on return
     c->n_pairs = n_pairs; c->n_frames = 2 * n_pairs; c->uploaded = true; c->solved = false;
     return SF_OK;
 }
@@ -266,12 +301,16 @@ int sf_upload_sequence(sf_ctx* c, int n_frames, const float* depth, const float*
     if ((rc = upload_stack(c, c->a.pyr_d, 0, 1, n_frames, depth, in_space))) return rc;
     if ((rc = upload_stack(c, c->a.pyr_i, 0, 1, n_frames, inten, in_space))) return rc;
     const int n_pairs = n_frames - 1;
-    std::vector<int> ci(n_pairs), pi(n_pairs);
-    for (int k = 0; k < n_pairs; k++) { ci[k] = k + 1; pi[k] = k; }  // prediction := previous raw frame
+    std::vector<int>&ci = c->h_ci, &pi = c->h_pi;
+    if ((int)ci.size() != n_pairs || ci[0] != 1 || pi[0] != 0) {
+        CU(cudaStreamSynchronize(c->stream));
+        ci.resize(n_pairs); pi.resize(n_pairs);
+        for (int k = 0; k < n_pairs; k++) { ci[k] = k + 1; pi[k] = k; }  // prediction := previous raw frame
+    }
     CU(cudaMemcpyAsync(c->d_cur_idx, ci.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
-    CU(cudaStreamSynchronize(c->stream));
+    if (twist_old_in) CU(cudaStreamSynchronize(c->stream));
     c->n_pairs = n_pairs; c->n_frames = n_frames; c->uploaded = true; c->solved = false;
     return SF_OK;
 }
@@ -284,24 +323,28 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
     const Arena& a = c->a;
     const DevParams& dp = c->dp;
     int n = 0;
-    n += launch_init_pairs(a, dp, c->d_twist_in, cfg);
-    if (build_pyramids) n += launch_pyramids(a, c->geom, c->levels, cfg);
-    n += launch_kmeans(a, dp, c->geom, c->levels, cfg);
+    c->prof.clear();
+    c->ev_used = 0;
+    { ProfScope ps(c, 0, 0); n += launch_init_pairs(a, dp, c->d_twist_in, cfg); }
+    if (build_pyramids) { ProfScope ps(c, 1, 0); n += launch_pyramids(a, c->geom, c->levels, cfg); }
+    { ProfScope ps(c, 2, 0); n += launch_kmeans(a, dp, c->geom, c->levels, cfg); }
     bool stop = false;
     for (int i = 0; i < c->levels && !stop; i++)
         for (int k = 0; k < c->p.max_iter_per_level && !stop; k++) {
             const int image_level = c->levels - i - 1;  // FrontEnd.cpp:1100
             const LevelGeom& g = c->geom[image_level];
             const int first = (i == 0 && k == 0) ? 1 : 0;
-            n += launch_step_begin(a, i, k, cfg);
-            if (!first) n += launch_warp(a, g, cfg);
-            n += launch_linearise(a, dp, g, first, cfg);
-            n += launch_step_prep(a, dp, i, k, cfg);
+            if (!first) { ProfScope ps(c, 3, image_level); n += launch_step_begin(a, i, k, cfg); n += launch_warp(a, g, cfg); }
+            else n += launch_step_begin(a, i, k, cfg);
+            { ProfScope ps(c, 4, image_level); n += launch_linearise(a, dp, g, first, cfg); n += launch_step_prep(a, dp, i, k, cfg); }
             if (i * c->p.max_iter_per_level + k == c->stop_step) { stop = true; break; }
-            for (int it = 1; it <= c->p.max_iter_irls; it++) n += launch_irls_iteration(a, dp, g, i, k, it, cfg);
-            n += launch_pose_update(a, dp, i, k, cfg);
+            for (int it = 1; it <= c->p.max_iter_irls; it++) {
+                { ProfScope ps(c, 5, image_level); n += launch_irls_pass1(a, dp, g, i, k, it, cfg); }
+                { ProfScope ps(c, 6, image_level); n += launch_irls_pass2(a, dp, g, i, k, it, cfg); }
+            }
+            { ProfScope ps(c, 7, image_level); n += launch_pose_update(a, dp, i, k, cfg); }
         }
-    n += launch_finish(a, dp, c->geom[0], cfg);
+    { ProfScope ps(c, 8, 0); n += launch_finish(a, dp, c->geom[0], cfg); }
     c->launches = n;
     CU(cudaGetLastError());
     return SF_OK;
@@ -473,6 +516,41 @@ int sf_get_outputs(sf_ctx* c, float T_odometry[16], float twist_old_out[6], floa
             if (b_perpixel) b_perpixel[dst] = bp[src];
             if (labels) labels[dst] = (int32_t)lb[src];
         }
+    return SF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement hooks
+// ---------------------------------------------------------------------------------------------
+int sf_profile_enable(sf_ctx* c, int on) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    c->prof_on = on != 0;
+    return SF_OK;
+}
+
+int sf_profile_read(sf_ctx* c, float* ms, int* launches) {
+    if (!c || !ms || !launches) return fail(SF_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < SF_PROF_CLASSES * SF_PROF_LEVELS; i++) { ms[i] = 0.f; launches[i] = 0; }
+    for (const auto& r : c->prof) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cls * SF_PROF_LEVELS + r.level] += t;
+        launches[r.cls * SF_PROF_LEVELS + r.level] += 1;
+    }
+    return SF_OK;
+}
+
+int sf_get_step_stats(sf_ctx* c, int* n_valid, int* irls_iters) {
+    if (!c || !n_valid || !irls_iters) return fail(SF_E_INVALID, "NULL argument");
+    if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->n_pairs * c->a.trace_steps;
+    std::vector<int> h(2 * n);
+    CU(cudaMemcpy(h.data(), c->a.stepstat, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) { n_valid[i] = h[2 * i]; irls_iters[i] = h[2 * i + 1]; }
     return SF_OK;
 }
 

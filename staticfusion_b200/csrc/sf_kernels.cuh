@@ -34,6 +34,7 @@ struct Arena {
     PairOut* out;               // [F]
     float* b_perpixel;          // [F][P0]
     float* trace;               // [F][steps][SF_TRACE_STEP] or nullptr
+    int* stepstat;              // [F][steps][2]: valid pixels, IRLS iterations
     size_t P0;                  // pixels of level 0
     int max_blocks;
     int trace_steps;
@@ -55,7 +56,8 @@ int launch_step_begin(const Arena& a, int level_i, int k, const LaunchCfg& c);
 int launch_warp(const Arena& a, const LevelGeom& g, const LaunchCfg& c);
 int launch_linearise(const Arena& a, const DevParams& p, const LevelGeom& g, int first, const LaunchCfg& c);
 int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
-int launch_irls_iteration(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
+int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
+int launch_irls_pass2(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
 int launch_pose_update(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
 int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const LaunchCfg& c);
 

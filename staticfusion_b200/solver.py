@@ -51,12 +51,19 @@ def _addr(x):
 class BatchResult:
     __slots__ = ("T", "twist_old", "b_segm", "b_perpixel", "labels", "irls_iters", "status")
 
-    def __init__(self, n, rows, cols, want_images):
+    def __init__(self, n, rows, cols, want_images, pinned=False):
         self.T = np.zeros((n, 16), np.float32)  # column-major 4x4 each (Eigen::Matrix4f)
         self.twist_old = np.zeros((n, 6), np.float32)
         self.b_segm = np.zeros((n, NUM_CLUSTERS), np.float32)
-        self.b_perpixel = np.zeros((n, rows, cols), np.float32) if want_images else None
-        self.labels = np.zeros((n, rows, cols), np.uint8) if want_images else None
+        self.b_perpixel = self.labels = None
+        if want_images:
+            if pinned:  # page-locked destination buffers: device->host copies run at full PCIe rate
+                import torch
+                self.b_perpixel = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True).numpy()
+                self.labels = torch.empty((n, rows, cols), dtype=torch.uint8, pin_memory=True).numpy()
+            else:
+                self.b_perpixel = np.zeros((n, rows, cols), np.float32)
+                self.labels = np.zeros((n, rows, cols), np.uint8)
         self.irls_iters = np.zeros(n, np.int32)
         self.status = np.zeros(n, np.int32)
 
@@ -136,14 +143,16 @@ class StaticFusionSolver:
         self.b_segm_perpixel, self.clusterAllocation0 = bp, lb
 
     # ---- batched path ----
-    def solve_batch(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None, want_images=True) -> BatchResult:
+    def solve_batch(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None, want_images=True, out=None) -> BatchResult:
         n = int(depth_cur.shape[0])
         a = [_addr(x) for x in (depth_cur, inten_cur, depth_pred, inten_pred)]
         space = a[0][1]
         if any(s != space for _, s, _ in a):
             raise ValueError("all image stacks must live in the same memory space")
-        r = BatchResult(n, self.rows, self.cols, want_images)
+        r = out if out is not None else BatchResult(n, self.rows, self.cols, want_images)
+        want_images = r.b_perpixel is not None
         tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        self._n = n
         check(self.L.sf_solve_batch(
             self.h, n, a[0][0], a[1][0], a[2][0], a[3][0], space, None if tw is None else _fp(tw),
             _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
@@ -158,6 +167,7 @@ class StaticFusionSolver:
             raise ValueError("all image stacks must live in the same memory space")
         r = BatchResult(nf - 1, self.rows, self.cols, want_images)
         tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        self._n = nf - 1
         check(self.L.sf_solve_sequence(
             self.h, nf, a[0][0], a[1][0], a[0][1], None if tw is None else _fp(tw),
             _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
@@ -201,6 +211,26 @@ class StaticFusionSolver:
     @property
     def last_launch_count(self) -> int:
         return int(self.L.sf_last_launch_count(self.h))
+
+    # ---- measurement hooks ----
+    def profile_enable(self, on: bool = True):
+        check(self.L.sf_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """(ms, launches) arrays of shape (classes, levels) for the last launch (call after sync)."""
+        n = _lib.PROF_CLASSES * _lib.PROF_LEVELS
+        ms = np.zeros(n, np.float32)
+        cnt = np.zeros(n, np.int32)
+        check(self.L.sf_profile_read(self.h, _fp(ms), _ip(cnt)))
+        return ms.reshape(_lib.PROF_CLASSES, _lib.PROF_LEVELS), cnt.reshape(_lib.PROF_CLASSES, _lib.PROF_LEVELS)
+
+    def step_stats(self):
+        """(n_valid, irls_iters) int arrays of shape (n_pairs, steps) for the last solve."""
+        steps = self.params.ctf_levels * self.params.max_iter_per_level
+        nv = np.zeros((self._n, steps), np.int32)
+        it = np.zeros((self._n, steps), np.int32)
+        check(self.L.sf_get_step_stats(self.h, _ip(nv), _ip(it)))
+        return nv, it
 
     # ---- introspection (parity tests) ----
     def debug_set_stop_step(self, step: int):
