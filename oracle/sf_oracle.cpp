@@ -959,6 +959,10 @@ void orc_ctx::solveOdometryAndSegmJoint() {
     const float inv_max_c = 1.f / max_wc_raw, inv_max_d = 1.f / max_wd_raw;
 
     std::vector<float> A(2 * N * 6), B(2 * N), res(2 * N);
+    /* EXACT / F64 policies: rows built with the RAW pre-weights; the 1/max normalisation (:505-509) is applied to the
+     * residual and folded into the robust weight instead of into every row entry (one rounding different per entry,
+     * far below the integer quantisation; lets the CUDA path store the rows once per linearisation). */
+    std::vector<float> Araw, Braw;
     std::vector<int> lab(N);
     const float f_inv = float(cols_i) / (2.f * std::tan(0.5f * p.fovh));
     /* the two Jacobian rows of a pixel, :545-585; wc_n / wd_n are the (normalised) pre-weights */
@@ -1001,7 +1005,11 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         if (exact) {
             fixBc += fixq(weights_c(v, u) * std::fabs(dct(v, u)), 32);
             fixBd += fixq(weights_d(v, u) * std::fabs(ddt(v, u)), 32);
-            float ac[6], ad[6], bc, bd;
+            if (Araw.empty()) { Araw.resize(2 * N * 6); Braw.resize(2 * N); }
+            float* ac = &Araw[(cont - 2) * 6];
+            float* ad = &Araw[(cont - 1) * 6];
+            float& bc = Braw[cont - 2];
+            float& bd = Braw[cont - 1];
             build_rows(v, u, weights_c(v, u), weights_d(v, u), ac, bc, ad, bd);
             for (int c = 0; c < 6; c++) { Mc[c] = std::max(Mc[c], std::fabs(ac[c])); Md[c] = std::max(Md[c], std::fabs(ad[c])); }
             Mc[6] = std::max(Mc[6], std::fabs(bc)); Md[6] = std::max(Md[6], std::fabs(bd));
@@ -1022,7 +1030,7 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         for (size_t i = 0; i < 2 * N; i++) { res[i] = -B[i]; s += std::fabs(res[i]); }
         aver_res = s / float(2 * N);
     } else {
-        for (size_t i = 0; i < 2 * N; i++) res[i] = -B[i];
+        for (size_t i = 0; i < 2 * N; i++) res[i] = ((i & 1) ? inv_max_d : inv_max_c) * (-Braw[i]);
         const double sc = (double)inv_max_c * (double)p.k_photometric_res;
         aver_res = (float)((sc * fixval(fixBc, 32) + (double)inv_max_d * fixval(fixBd, 32)) / (double)(2 * N));
     }
@@ -1053,13 +1061,21 @@ void orc_ctx::solveOdometryAndSegmJoint() {
             for (int r = 0; r < 2; r++) { /* :627-636 */
                 const size_t row = 2 * n + r;
                 const float w = b_weight * sqrtf(1.f / (1.f + sq(res[row] * inv_c_Cauchy)));
-                float aw[6];
-                for (int c = 0; c < 6; c++) aw[c] = w * A[row * 6 + c];
-                const float bw = w * B[row];
+                float aw[6], bw;
+                if (exact) { /* normalisation folded into the weight: (w * inv_max) * raw entry */
+                    const float wm = w * (r ? inv_max_d : inv_max_c);
+                    for (int c = 0; c < 6; c++) aw[c] = wm * Araw[row * 6 + c];
+                    bw = wm * Braw[row];
+                } else {
+                    for (int c = 0; c < 6; c++) aw[c] = w * A[row * 6 + c];
+                    bw = w * B[row];
+                }
                 if (quant) {
+                    /* (w * (inv_max * 2^s)) * raw entry: the power of two commutes with the rounding */
                     float aws[6];
-                    for (int c = 0; c < 6; c++) aws[c] = ldexpf(aw[c], sexp[c]);
-                    const float bws = ldexpf(bw, sexp[6]);
+                    const float im = r ? inv_max_d : inv_max_c;
+                    for (int c = 0; c < 6; c++) aws[c] = (w * ldexpf(im, sexp[c])) * Araw[row * 6 + c];
+                    const float bws = (w * ldexpf(im, sexp[6])) * Braw[row];
                     for (int i = 0; i < 6; i++) {
                         for (int j = i; j < 6; j++) {
                             const int64_t q = qprod(aws[i], aws[j]);
@@ -1112,9 +1128,15 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         if (nz) status |= 4;
         /* :644-646 */
         for (size_t i = 0; i < 2 * N; i++) {
-            float r = -B[i];
-            for (int c = 0; c < 6; c++) r += Var[c] * A[i * 6 + c];
-            res[i] = r;
+            if (exact) {
+                float r = -Braw[i];
+                for (int c = 0; c < 6; c++) r += Var[c] * Araw[i * 6 + c];
+                res[i] = ((i & 1) ? inv_max_d : inv_max_c) * r;
+            } else {
+                float r = -B[i];
+                for (int c = 0; c < 6; c++) r += Var[c] * A[i * 6 + c];
+                res[i] = r;
+            }
         }
         /* :650-667 */
         float aver_res_label[NC];
@@ -1132,7 +1154,8 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         }
         for (size_t n = 0; n < N; n++) {
             const float ress_here = std::fabs(res[2 * n]) + std::fabs(res[2 * n + 1]);
-            if (exact) fix_label[lab[n]] += fixq(ress_here, 30);
+            if (quant) fix_label[lab[n]] += (int64_t)std::nearbyint((double)ress_here * std::ldexp(1.0, rexp + 9));
+            else if (exact) fix_label[lab[n]] += fixq(ress_here, 30);
             else aver_res_label[lab[n]] += ress_here;
             num_pix_label[lab[n]]++;
             if (quant) {
@@ -1143,8 +1166,9 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         }
         if (exact) {
             int64_t tot = 0;
-            for (int l = 0; l < NC; l++) { tot += fix_label[l]; aver_res_label[l] = (float)fixval(fix_label[l], 30); }
-            aver_res = (float)fixval(tot, 30) / float(2 * N);
+            const int ls = quant ? rexp + 9 : 30; /* EXACT: |res_c|+|res_d| < 2^(11-rexp), so the scaled term stays below 2^20 */
+            for (int l = 0; l < NC; l++) { tot += fix_label[l]; aver_res_label[l] = (float)fixval(fix_label[l], ls); }
+            aver_res = (float)fixval(tot, ls) / float(2 * N);
             res_sq = quant ? std::ldexp((double)rs_q, -2 * rexp) : rs_d;
         } else {
             float tot = 0.f;

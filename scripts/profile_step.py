@@ -1,0 +1,32 @@
+"""One warm solve + one measured solve of a bench config, for ncu launch lists / captures.
+
+    ncu --metrics gpu__time_duration.sum --clock-control none -s <launches of one solve> -c <same> ... python scripts/profile_step.py [batch] [config]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+import staticfusion_b200 as sf
+
+
+def main():
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    config = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    name, rows, cols, levels, F, scene = bench.CONFIGS[config]
+    d, c = bench.make_frames(scene, 17, rows, cols)
+    pidx, cidx = bench.pair_indices(batch, 17)
+    g = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (d[cidx], c[cidx], d[pidx], c[pidx])]
+    s = sf.StaticFusionSolver(sf.default_params(rows, cols, ctf_levels=levels), max_batch=batch)
+    for _ in range(2):
+        s.upload_pairs(*g)
+        s.launch()
+        s.sync()
+    print("launches per solve:", s.last_launch_count)
+
+
+if __name__ == "__main__":
+    main()

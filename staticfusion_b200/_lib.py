@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstaticfusion_b200.so")
+LIB_PATH = os.environ.get("SF_B200_LIB") or os.path.join(_HERE, "lib", "libstaticfusion_b200.so")  # env override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 NUM_CLUSTERS = 24

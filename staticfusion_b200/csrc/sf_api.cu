@@ -182,6 +182,11 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
         if (nb > mb) mb = nb;
     }
     a.max_blocks = mb;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return fail(SF_E_CUDA, "cudaGetDeviceProperties failed"); }
+        a.num_sms = prop.multiProcessorCount;
+    }
     a.trace_steps = p->ctf_levels * p->max_iter_per_level;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(SF_E_CUDA, cudaGetErrorString(e)); }
@@ -197,8 +202,9 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.acc_iw, sizeof(unsigned long long) * a.P0 * F);
     ok = ok && alloc((void**)&a.warp_d, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
-    ok = ok && alloc((void**)&a.lin, sizeof(float) * NPLANES * a.P0 * F);
-    ok = ok && alloc((void**)&a.vlabel, a.P0 * F);
+    ok = ok && alloc((void**)&a.tiles, tiles_per_pair(a.P0) * TILE_BYTES * F);
+    ok = ok && alloc((void**)&a.gcount, sizeof(int) * 2);
+    if (ok && (flags & 1)) ok = alloc((void**)&a.dbg, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
     ok = ok && alloc((void**)&a.b_perpixel, sizeof(float) * a.P0 * F);
@@ -213,8 +219,9 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     // splat accumulators are kept zero between uses (warp_normalise clears what it reads)
     cudaMemsetAsync(a.acc_d, 0, sizeof(long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
-    cudaMemsetAsync(a.vlabel, 0xff, a.P0 * F, c->stream);
-    cudaMemsetAsync(a.lin, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
+    cudaMemsetAsync(a.tiles, 0xff, tiles_per_pair(a.P0) * TILE_BYTES * F, c->stream);  // every label byte = invalid
+    cudaMemsetAsync(a.gcount, 0, sizeof(int) * 2, c->stream);
+    if (a.dbg) cudaMemsetAsync(a.dbg, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
     c->h_out.resize(F);
@@ -228,8 +235,8 @@ void sf_destroy(sf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     Arena& a = c->a;
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
-    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.lin);
-    cudaFree(a.vlabel); cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
+    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount);
+    cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
     cudaFree(a.trace); cudaFree(a.stepstat);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -584,16 +591,20 @@ int sf_debug_get_plane(sf_ctx* c, const char* name, int pair, int image_level, f
     else {
         static const char* names[NPLANES] = {"depth_inter", "xx_inter", "yy_inter", "dcu", "dcv", "dct", "ddu", "ddv", "ddt", "weights_c", "weights_d"};
         for (int k = 0; k < NPLANES; k++)
-            if (n == names[k]) src = a.lin + ((size_t)pair * NPLANES + k) * a.P0;
+            if (n == names[k]) {
+                if (!a.dbg) return fail(SF_E_STATE, "linearisation planes are only kept when the context was created with the trace flag");
+                src = a.dbg + ((size_t)pair * NPLANES + k) * a.P0;
+            }
     }
     if (src) {
         CU(cudaMemcpy(out, src, sizeof(float) * g.P, cudaMemcpyDeviceToHost));
         return SF_OK;
     }
     if (n == "valid") {
-        std::vector<uint8_t> v(g.P);
-        CU(cudaMemcpy(v.data(), a.vlabel + (size_t)pair * a.P0, g.P, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < g.P; i++) out[i] = (v[i] != VLABEL_INVALID) ? 1.f : 0.f;
+        const size_t nt = tiles_per_pair((size_t)g.P);
+        std::vector<uint8_t> v(nt * TILE_BYTES);
+        CU(cudaMemcpy(v.data(), a.tiles + (size_t)pair * tiles_per_pair(a.P0) * TILE_BYTES, v.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < g.P; i++) out[i] = (v[tile_label_off(i)] != VLABEL_INVALID) ? 1.f : 0.f;
         return SF_OK;
     }
     return fail(SF_E_INVALID, "unknown plane name");

@@ -16,10 +16,26 @@ namespace sf {
 
 constexpr int NC = SF_NUM_CLUSTERS;
 constexpr int MAX_LEVELS = 8;
-constexpr int NPLANES = 11;  // d, x, y, dcu, dcv, dct, ddu, ddv, ddt, wc, wd
+constexpr int NPLANES = 11;  // debug planes: d, x, y, dcu, dcv, dct, ddu, ddv, ddt, wc, wd (only kept when tracing)
 enum Plane { PL_D = 0, PL_X, PL_Y, PL_DCU, PL_DCV, PL_DCT, PL_DDU, PL_DDV, PL_DDT, PL_WC, PL_WD };
+// the two Jacobian rows of a pixel built with the RAW pre-weights (FrontEnd.cpp:552-585): what the IRLS passes stream
+constexpr int NROWPL = 14;   // colour row a0..a5, colour rhs b, depth row a0..a5, depth rhs b
+constexpr int RW_AC = 0, RW_BC = 6, RW_AD = 7, RW_BD = 13;
 constexpr uint8_t LABEL_NONE = NC;      // no depth (clusterAllocation value 24, KMeans.cpp:70)
 constexpr uint8_t VLABEL_INVALID = 255; // pixel not in validPixels (FrontEnd.cpp:417)
+
+// Rows are stored as TILES: one 64-pixel tile = 14 planes x 64 floats followed by the 64 label bytes of those pixels
+// (255 = not in validPixels), 3648 contiguous bytes.  One tile = one cp.async.bulk (TMA bulk copy) into shared memory.
+constexpr int ROW_TILE = 64;
+constexpr int TILE_ROW_BYTES = ROW_TILE * NROWPL * 4;    // 3584
+constexpr int TILE_BYTES = TILE_ROW_BYTES + ROW_TILE;    // 3648 (multiple of 16)
+__host__ __device__ __forceinline__ size_t tiles_per_pair(size_t P0) { return (P0 + ROW_TILE - 1) / ROW_TILE; }
+__host__ __device__ __forceinline__ size_t tile_row_off(int k, int p) {   // byte offset of row plane k of pixel p
+    return (size_t)(p / ROW_TILE) * TILE_BYTES + ((size_t)k * ROW_TILE + (size_t)(p % ROW_TILE)) * 4;
+}
+__host__ __device__ __forceinline__ size_t tile_label_off(int p) {        // byte offset of the label of pixel p
+    return (size_t)(p / ROW_TILE) * TILE_BYTES + TILE_ROW_BYTES + (size_t)(p % ROW_TILE);
+}
 
 // fixed-point scales of the order-independent sums (mirrored by the oracle's EXACT policy)
 constexpr int FIX_KMEANS = 36;  // k-means centre sums (KMeans.cpp:215)
@@ -83,6 +99,7 @@ struct PairCtl {
     unsigned colmax_c[7], colmax_d[7];  // max |row entry| per column (6 Jacobian columns + rhs) with raw weights, float bits
     float colbound[7];                  // bound of the normalised columns
     int sexp[7];                        // power-of-two column scales
+    float mcs[7], mds[7];               // inv_max_c * 2^sexp[k], inv_max_d * 2^sexp[k] (exact scalings)
     int rexp;                           // power-of-two scale of the residuals
     long long acc_ne[27];               // integer normal equations: 21 upper-triangular AtA terms + 6 AtB terms
     long long acc_rs;                   // integer |res|^2

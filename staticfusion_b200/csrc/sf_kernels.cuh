@@ -28,8 +28,9 @@ struct Arena {
     unsigned long long* acc_iw; // [F][P0] packed: weight sum (high 22 bits) | intensity sum (low 42 bits, 2^22)
     float* warp_d;              // [F][P0]
     float* warp_i;              // [F][P0]
-    float* lin;                 // [F][NPLANES][P0]
-    uint8_t* vlabel;            // [F][P0]
+    uint8_t* tiles;             // [F][tiles_per_pair(P0)][TILE_BYTES] raw Jacobian rows + valid-pixel labels
+    float* dbg;                 // [F][NPLANES][P0] linearisation planes, only with the trace flag (else nullptr)
+    int* gcount;                // [2]: pairs active in the current step, pairs still inside the IRLS loop
     PairCtl* ctl;               // [F]
     PairOut* out;               // [F]
     float* b_perpixel;          // [F][P0]
@@ -37,6 +38,7 @@ struct Arena {
     int* stepstat;              // [F][steps][2]: valid pixels, IRLS iterations
     size_t P0;                  // pixels of level 0
     int max_blocks;
+    int num_sms;
     int trace_steps;
 };
 
