@@ -18,11 +18,11 @@ def main():
     config = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     name, rows, cols, levels, F, scene = bench.CONFIGS[config]
     d, c = bench.make_frames(scene, 17, rows, cols)
-    pidx, cidx = bench.pair_indices(batch, 17)
-    g = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (d[cidx], c[cidx], d[pidx], c[pidx])]
+    seq = bench.sequence_indices(batch + 1, 17)
+    g = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (d[seq], c[seq])]
     s = sf.StaticFusionSolver(sf.default_params(rows, cols, ctf_levels=levels), max_batch=batch)
     for _ in range(2):
-        s.upload_pairs(*g)
+        s.upload_sequence(*g)
         s.launch()
         s.sync()
     print("launches per solve:", s.last_launch_count)

@@ -51,7 +51,16 @@ struct sf_ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    // the static schedule captured once per (batch shape, stop step) and replayed: removes ~500 launch gaps per solve
+    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids; cudaGraphExec_t exec; int launches; };
+    std::vector<GraphRec> graphs;
+    bool use_graph = true;
 };
+
+static void drop_graphs(sf_ctx* c) {
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
 
 static cudaEvent_t prof_event(sf_ctx* c) {
     if (c->ev_used == c->ev_pool.size()) {
@@ -224,6 +233,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     if (a.dbg) cudaMemsetAsync(a.dbg, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
+    sf::prepare_kernels();
     c->h_out.resize(F);
     *out = c;
     return SF_OK;
@@ -238,6 +248,7 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
     cudaFree(a.trace); cudaFree(a.stepstat);
+    drop_graphs(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -252,6 +263,7 @@ int sf_set_params(sf_ctx* c, const sf_params* p) {
     if (p->enable_segmentation && c->p.ctf_levels < 2) return fail(SF_E_INVALID, "segmentation needs ctf_levels >= 2");
     c->p = *p;
     fill_dev_params(c);
+    drop_graphs(c);  // kernel arguments are baked into captured graphs
     return SF_OK;
 }
 
@@ -357,11 +369,34 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
     return SF_OK;
 }
 
+static int launch_solve(sf_ctx* c, bool build_pyramids) {
+    if (c->prof_on || !c->use_graph) return enqueue_solve(c, build_pyramids);  // per-kernel events need plain launches
+    for (const auto& g : c->graphs)
+        if (g.n_pairs == c->n_pairs && g.n_frames == c->n_frames && g.stop_step == c->stop_step && g.pyramids == (int)build_pyramids) {
+            CU(cudaGraphLaunch(g.exec, c->stream));
+            c->launches = g.launches;
+            return SF_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_solve(c, build_pyramids);
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != SF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(SF_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return fail(SF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2));
+    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, exec, c->launches});
+    CU(cudaGraphLaunch(exec, c->stream));
+    return SF_OK;
+}
+
 int sf_launch(sf_ctx* c) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->uploaded) return fail(SF_E_STATE, "no batch uploaded");
     CU(cudaSetDevice(c->device));
-    const int rc = enqueue_solve(c, true);
+    const int rc = launch_solve(c, true);
     if (rc == SF_OK) c->solved = true;
     return rc;
 }
@@ -491,7 +526,7 @@ int sf_run_solver(sf_ctx* c, int create_image_pyr) {
     CU(cudaMemcpyAsync(c->d_twist_in, c->h_twist_old, sizeof(float) * 6, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->n_pairs = 1; c->n_frames = 2; c->uploaded = true;
-    rc = enqueue_solve(c, false);
+    rc = launch_solve(c, false);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     c->solved = true;

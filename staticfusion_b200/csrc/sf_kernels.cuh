@@ -48,6 +48,7 @@ struct LaunchCfg {
     int n_frames;
 };
 
+void prepare_kernels();     // one-time kernel attribute setup (dynamic shared memory sizes); call outside stream capture
 int irls_chunk_iters(int P);  // deterministic function of the level size only
 
 // every launcher returns the number of kernels it enqueued

@@ -257,3 +257,50 @@ class StaticFusionSolver:
         out = np.zeros(n, np.float32)
         check(self.L.sf_debug_get_trace(self.h, pair, _fp(out), n))
         return out.reshape(-1, TRACE_STEP)
+
+
+class PipelinedSolver:
+    """Frame-to-frame odometry over a long host-resident sequence with copies and compute overlapped.
+
+    `n_ctx` solver contexts (each with its own CUDA stream and device arena) take turns on chunks of
+    `chunk` pairs: while one context solves, the next one's frames travel host->device and the previous
+    one's results travel back, all through the split-phase C ABI (sf_upload_sequence / sf_launch /
+    sf_download).  Pass page-locked buffers (``torch.Tensor.pin_memory()`` or ``BatchResult(pinned=True)``)
+    so the copies are truly asynchronous.  Results are bit-identical to one big ``solve_sequence`` call.
+    """
+
+    def __init__(self, params: SfParams | None = None, device: int = 0, chunk: int = 128, n_ctx: int = 3):
+        self.params = params if params is not None else default_params()
+        self.rows, self.cols = self.params.rows, self.params.cols
+        self.chunk = chunk
+        self.ctx = [StaticFusionSolver(self.params, device=device, max_batch=chunk) for _ in range(n_ctx)]
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def solve_sequence(self, depth, inten, out: BatchResult | None = None, want_images: bool = True) -> BatchResult:
+        n_pairs = int(depth.shape[0]) - 1
+        r = out if out is not None else BatchResult(n_pairs, self.rows, self.cols, want_images)
+        want_images = r.b_perpixel is not None
+        spans = [(s, min(s + self.chunk, n_pairs)) for s in range(0, n_pairs, self.chunk)]
+        L = self.ctx[0].L
+        pending = []  # (ctx, span) in flight
+
+        def drain(ctx, span):
+            s0, s1 = span
+            check(L.sf_download(
+                ctx.h, _fp(r.T[s0:s1]), _fp(r.twist_old[s0:s1]), _fp(r.b_segm[s0:s1]),
+                r.b_perpixel[s0:s1].ctypes.data if want_images else None, r.labels[s0:s1].ctypes.data if want_images else None,
+                MEM_HOST, _ip(r.irls_iters[s0:s1]), _ip(r.status[s0:s1])))
+
+        for k, (s0, s1) in enumerate(spans):
+            ctx = self.ctx[k % len(self.ctx)]
+            if len(pending) == len(self.ctx):  # this context is still busy with an older chunk: collect it first
+                drain(*pending.pop(0))
+            ctx.upload_sequence(depth[s0:s1 + 1], inten[s0:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
+            ctx.launch()
+            pending.append((ctx, (s0, s1)))
+        while pending:
+            drain(*pending.pop(0))
+        return r
