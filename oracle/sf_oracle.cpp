@@ -111,9 +111,9 @@ void ldlt_solve_factored(int n, const T* A, const unsigned char* zero, const T* 
         x[i] = s;
     }
     for (int i = 0; i < n; i++) x[i] = zero[i] ? (T)0 : x[i] / A[i * n + i];
-    for (int i = n - 1; i >= 0; i--) {
+    for (int i = n - 1; i >= 0; i--) { /* descending k: the order a column sweep produces (x_k is used as soon as it is final) */
         T s = x[i];
-        for (int k = i + 1; k < n; k++) s -= A[k * n + i] * x[k];
+        for (int k = n - 1; k > i; k--) s -= A[k * n + i] * x[k];
         x[i] = s;
     }
 }

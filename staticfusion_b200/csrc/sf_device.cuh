@@ -160,9 +160,9 @@ __device__ inline void ldlt_solve_factored(const double* A, const unsigned char*
         x[i] = s;
     }
     for (int i = 0; i < N; i++) x[i] = zero[i] ? 0.0 : x[i] / A[i * N + i];
-    for (int i = N - 1; i >= 0; i--) {
+    for (int i = N - 1; i >= 0; i--) {  // descending k, as in the oracle
         double s = x[i];
-        for (int k = i + 1; k < N; k++) s -= A[k * N + i] * x[k];
+        for (int k = N - 1; k > i; k--) s -= A[k * N + i] * x[k];
         x[i] = s;
     }
 }
@@ -186,19 +186,20 @@ __device__ inline void ldlt24_warp(double* A, double* rhs, double* x, unsigned c
         }
         __syncwarp();
     }
-    if (lane == 0) {
-        for (int i = 0; i < NC; i++) {
-            double s = rhs[i];
-            for (int k = 0; k < i; k++) s -= A[i * LD + k] * x[k];
-            x[i] = s;
-        }
-        for (int i = 0; i < NC; i++) x[i] = zero[i] ? 0.0 : x[i] / A[i * LD + i];
-        for (int i = NC - 1; i >= 0; i--) {
-            double s = x[i];
-            for (int k = i + 1; k < NC; k++) s -= A[k * LD + i] * x[k];
-            x[i] = s;
-        }
+    // triangular solves as column sweeps: lane i owns component i; every component sees the same sequence of
+    // subtractions as the serial code (forward: k ascending, backward: k descending)
+    double yi = (lane < NC) ? rhs[lane] : 0.0;
+    for (int k = 0; k < NC; k++) {
+        const double yk = __shfl_sync(0xffffffffu, yi, k);  // final: all its terms k' < k have been subtracted
+        if (lane > k && lane < NC) yi -= A[lane * LD + k] * yk;
     }
+    double xi = 0.0;
+    if (lane < NC) xi = zero[lane] ? 0.0 : yi / A[lane * LD + lane];
+    for (int k = NC - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(0xffffffffu, xi, k);
+        if (lane < k) xi -= A[k * LD + lane] * xk;
+    }
+    if (lane < NC) x[lane] = xi;
     __syncwarp();
 }
 
