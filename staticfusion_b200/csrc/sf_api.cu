@@ -213,6 +213,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.tiles, tiles_per_pair(a.P0) * TILE_BYTES * F);
     ok = ok && alloc((void**)&a.gcount, sizeof(int) * 2);
+    ok = ok && alloc((void**)&a.work_ctr, sizeof(int) * MAX_WORK_CTRS);
     if (ok && (flags & 1)) ok = alloc((void**)&a.dbg, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
@@ -245,7 +246,7 @@ void sf_destroy(sf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     Arena& a = c->a;
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
-    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount);
+    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.work_ctr);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
     cudaFree(a.trace); cudaFree(a.stepstat);
     drop_graphs(c);
@@ -338,7 +339,8 @@ int sf_upload_sequence(sf_ctx* c, int n_frames, const float* depth, const float*
 // schedule
 // ---------------------------------------------------------------------------------------------
 static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
-    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames};
+    int ctr = 0;
+    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames, &ctr};
     const Arena& a = c->a;
     const DevParams& dp = c->dp;
     int n = 0;
@@ -503,7 +505,7 @@ int sf_create_image_pyramid(sf_ctx* c, int old_im) {
     Arena a = c->a;
     a.pyr_d += (size_t)frame * a.pyr_stride;
     a.pyr_i += (size_t)frame * a.pyr_stride;
-    const LaunchCfg cfg{c->stream, 1, 1};
+    const LaunchCfg cfg{c->stream, 1, 1, nullptr};
     launch_pyramids(a, c->geom, c->levels, cfg);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));

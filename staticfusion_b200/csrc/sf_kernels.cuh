@@ -31,6 +31,7 @@ struct Arena {
     uint8_t* tiles;             // [F][tiles_per_pair(P0)][TILE_BYTES] raw Jacobian rows + valid-pixel labels
     float* dbg;                 // [F][NPLANES][P0] linearisation planes, only with the trace flag (else nullptr)
     int* gcount;                // [2]: pairs active in the current step, pairs still inside the IRLS loop
+    int* work_ctr;              // [MAX_WORK_CTRS] dynamic item counters, one per pass launch of a solve (zeroed by init_pairs)
     PairCtl* ctl;               // [F]
     PairOut* out;               // [F]
     float* b_perpixel;          // [F][P0]
@@ -42,10 +43,13 @@ struct Arena {
     int trace_steps;
 };
 
+constexpr int MAX_WORK_CTRS = 4096;
+
 struct LaunchCfg {
     cudaStream_t stream;
     int n_pairs;
     int n_frames;
+    int* next_ctr;  // host-side running index into Arena::work_ctr for this solve
 };
 
 void prepare_kernels();     // one-time kernel attribute setup (dynamic shared memory sizes); call outside stream capture
