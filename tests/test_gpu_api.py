@@ -134,3 +134,56 @@ def test_known_motion_recovered_at_full_size(gpu):
     # ~8 % under-estimated yaw accumulates, so this is a loose sanity bound, not an accuracy claim
     assert dt < 0.15 and dr < 0.12
     s.close()
+
+
+def test_pipelined_solver_is_bit_identical_to_one_call(gpu):
+    """PipelinedSolver overlaps copies and compute over several contexts; chunking must not change a bit."""
+    d, c = frames("dynamic", 12, 240, 320)
+    p = gpu.default_params(240, 320, ctf_levels=3)
+    one = gpu.StaticFusionSolver(p, max_batch=11)
+    ref = one.solve_sequence(d, c)
+    ps = gpu.PipelinedSolver(p, chunk=4, n_ctx=2)
+    out = gpu.BatchResult(11, 240, 320, True, pinned=True)
+    got = ps.solve_sequence(d, c, out=out)
+    assert same(ref, got)
+    got2 = ps.solve_sequence(d, c)  # second run reuses the captured graphs
+    assert same(ref, got2)
+    one.close()
+    ps.close()
+
+
+def test_parameter_change_takes_effect_after_graph_capture(gpu, oracle_mod):
+    """sf_set_params must invalidate the captured CUDA graphs (the drivers rewrite kb per frame,
+    StaticFusion-datasets.cpp:156-165)."""
+    from common import oracle_params_from
+    d, c = frames("dynamic", 2, 240, 320)
+    p = gpu.default_params(240, 320)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r1 = s.solve_sequence(d, c)
+    r1b = s.solve_sequence(d, c)  # replayed graph
+    assert same(r1, r1b)
+    p2 = gpu.default_params(240, 320, kb=1.05)  # bootstrap value, StaticFusion-datasets.cpp:121
+    s.set_params(p2)
+    r2 = s.solve_sequence(d, c)
+    assert not np.array_equal(r1.b_segm, r2.b_segm)
+    o = oracle_mod.Oracle(oracle_params_from(oracle_mod, p2), oracle_mod.ACCUM_EXACT)
+    o.solve_pair(d[1], c[1], d[0], c[0])
+    assert np.array_equal(r2.T_matrices()[0], o.T()) and np.array_equal(r2.b_segm[0], o.b_segm())
+    s.close()
+
+
+def test_stress_resolution_1280x960_smoke(gpu, oracle_mod):
+    """BASELINE config 5 shape (1280x960, 4 levels): one pair, parity against the oracle."""
+    from common import oracle_params_from
+    d, c = frames("dynamic", 2, 960, 1280)
+    p = gpu.default_params(960, 1280, ctf_levels=4)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r = s.solve_sequence(d, c)
+    o = oracle_mod.Oracle(oracle_params_from(oracle_mod, p), oracle_mod.ACCUM_EXACT)
+    o.solve_pair(d[1], c[1], d[0], c[0])
+    dt, dr = pose_error(r.T_matrices()[0], o.T())
+    assert dt <= 1e-5 and dr <= 1e-5
+    assert np.array_equal(r.labels[0].astype(np.int32), o.labels(0))
+    assert np.array_equal(r.b_perpixel[0] > 0.5, o.b_perpixel() > 0.5)
+    assert r.irls_iters[0] == o.total_irls()
+    s.close()
