@@ -137,25 +137,67 @@ def l0_equiv_iterations(n_valid, iters):
 # CPU arm: the oracle on the host cores
 # ------------------------------------------------------------------------------------------------
 _W = {}
+CPU_NOTE = {
+    "reference": "the reference's own KMeans.cpp / SegmentationBackground.cpp / FrontEnd.cpp:256-1146 / StaticFusion.h compiled unmodified "
+                 "with the reference's flags against oracle/ref_shim (stand-in for Eigen/MRPT, which are not installed)",
+    "port": "the oracle's reference-literal policy: plain-loop C++ port, -O3 -msse2 -msse3 -mtune=native, bit-identical to the reference's "
+            "own sources compiled against the header shim (tests/test_oracle_vs_reference.py); the shim build itself is not timed because "
+            "its eager Eigen temporaries would understate the reference's speed",
+}
+
+
+def cpu_kind(rows, cols):
+    """Which CPU implementation is TIMED.  The reference's own sources do run here (oracle/_ref, compiled against the header
+    shim) and the oracle's reference-literal policy is bit-identical to them (tests/test_oracle_vs_reference.py), but the
+    shim evaluates every Eigen expression eagerly with heap temporaries (e.g. one per Jacobian row at FrontEnd.cpp:628),
+    which real Eigen would not: timing it would understate the reference's speed and inflate the GPU/CPU ratio.  The
+    dependency-free port (same arithmetic, plain loops, the reference's compiler flags) is therefore the timed baseline;
+    set SF_BENCH_CPU=reference to time the shim build instead."""
+    if os.environ.get("SF_BENCH_CPU", "port") == "reference":
+        from oracle import reference as R
+        if R.available() and rows * 4 == cols * 3 and 480 % rows == 0 and 480 // rows in (1, 2, 4, 8):
+            try:
+                R.lib()
+                return "reference"
+            except (OSError, FileNotFoundError):
+                pass
+    return "port"
 
 
 def _cpu_init(rows, cols, levels):
-    from oracle import oracle as O
-    _W["O"] = O
-    _W["o"] = O.Oracle(O.driver_params(rows, cols, ctf_levels=levels), O.ACCUM_F32)  # reference-literal float sums
+    if cpu_kind(rows, cols) == "reference":
+        from oracle import reference as R
+        _W["kind"] = "reference"
+        _W["o"] = R.Reference(480 // rows, ctf_levels=levels)  # driver parameters, StaticFusion-datasets.cpp:79-94
+        _W["levels"] = levels
+    else:
+        from oracle import oracle as O
+        _W["kind"] = "port"
+        _W["o"] = O.Oracle(O.driver_params(rows, cols, ctf_levels=levels), O.ACCUM_F32)  # reference-literal float sums
 
 
 def _cpu_solve(job):
-    dc, ic, dp, ip = job
-    O, o = _W["O"], _W["o"]
-    o.solve_pair(dc, ic, dp, ip)
-    tr = o.trace()
-    return tr[:, 3].astype(np.int64), tr[:, 4].astype(np.int64)
+    dc, ic, dp, ip, nv, it = job
+    _W["o"].solve_pair(dc, ic, dp, ip)
+    return nv, it  # iteration counts come from the GPU run of the same pairs (identical by the parity tests)
 
 
-def cpu_run(d, c, pidx, cidx, rows, cols, levels, nproc):
-    """Solve the listed pairs with nproc oracle processes; returns (seconds, finest-equivalent iterations, pairs)."""
-    jobs = [(d[j], c[j], d[i], c[i]) for i, j in zip(pidx, cidx)]
+def cpu_run(d, c, pidx, cidx, rows, cols, levels, nproc, stats=None):
+    """Solve the listed pairs on the CPU with nproc processes; returns (seconds, finest-equivalent iterations, pairs).
+    `stats` = (n_valid, irls_iters) per pair and step; measured with the oracle when not given."""
+    if stats is None:
+        from oracle import oracle as O
+        nvs, its = [], []
+        o = O.Oracle(O.driver_params(rows, cols, ctf_levels=levels), O.ACCUM_F32)
+        seen = {}
+        for i, j in zip(pidx, cidx):
+            if (i, j) not in seen:
+                o.solve_pair(d[j], c[j], d[i], c[i])
+                tr = o.trace()
+                seen[(i, j)] = (tr[:, 3].astype(np.int64), tr[:, 4].astype(np.int64))
+            nvs.append(seen[(i, j)][0]); its.append(seen[(i, j)][1])
+        stats = (np.stack(nvs), np.stack(its))
+    jobs = [(d[j], c[j], d[i], c[i], stats[0][k], stats[1][k]) for k, (i, j) in enumerate(zip(pidx, cidx))]
     if nproc == 1:
         _cpu_init(rows, cols, levels)
         t0 = time.perf_counter()
@@ -216,9 +258,9 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfg, "frames_per_s": tot_pairs / tot_t,
-                "cpu_baseline": {"value": v, "unit": unit, "cores": nproc, "kind": "port",
-                                 "sample": f"{per_step} pairs per step x {a.steps} steps of the workload, one oracle process per core "
-                                           "(reference-literal float accumulation; the reference itself cannot be built here)"},
+                "cpu_baseline": {"value": v, "unit": unit, "cores": nproc, "kind": cpu_kind(rows, cols),
+                                 "sample": f"{per_step} pairs per step x {a.steps} steps of the workload, one single-threaded solver process per core; "
+                                           + CPU_NOTE[cpu_kind(rows, cols)]},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -371,12 +413,11 @@ def main():
                 "host_wall_ms_per_step": 1e3 * t_host / a.steps}
         if not a.no_cpu_baseline:
             # bounded single-thread sample (the reference is single-threaded): ~10 s of CPU work
-            dt, eq, n = cpu_run(d, c, pidx[:4], cidx[:4], rows, cols, levels, 1)
+            dt, eq, n = cpu_run(d, c, pidx[:4], cidx[:4], rows, cols, levels, 1, stats=(nv[:4], it[:4]))
             n_s = int(min(max(16, 10.0 / (dt / n)), F))
-            dt, eq, n = cpu_run(d, c, pidx[:n_s], cidx[:n_s], rows, cols, levels, 1)
-            line["cpu_baseline"] = {"value": eq / dt, "unit": unit, "cores": 1, "kind": "port", "frames_per_s": n / dt,
-                                    "sample": f"first {n} pairs of the batch, single thread, reference-literal float accumulation "
-                                              f"({dt:.1f} s); the reference itself cannot be built here"}
+            dt, eq, n = cpu_run(d, c, pidx[:n_s], cidx[:n_s], rows, cols, levels, 1, stats=(nv[:n_s], it[:n_s]))
+            line["cpu_baseline"] = {"value": eq / dt, "unit": unit, "cores": 1, "kind": cpu_kind(rows, cols), "frames_per_s": n / dt,
+                                    "sample": f"first {n} pairs of the batch, single thread ({dt:.1f} s); " + CPU_NOTE[cpu_kind(rows, cols)]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

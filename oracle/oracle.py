@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/sf_oracle.{h,cpp}).
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see sf_oracle.h).  Importable from tests/,
+TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own sources (see sf_oracle.h, oracle/reference.py).  Importable from tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never from
 the product package.
 """

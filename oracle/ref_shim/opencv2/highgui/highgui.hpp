@@ -1,0 +1,2 @@
+/* forwards to the shim: see sf_ref_shim.h */
+#include "../../sf_ref_shim.h"

@@ -1,0 +1,189 @@
+"""ctypes binding of oracle/_ref/libsf_ref.so: the REFERENCE's own solver sources (KMeans.cpp,
+SegmentationBackground.cpp, FrontEnd.cpp lines 256-1146, StaticFusion.h), compiled unmodified from
+/root/reference against the header shim in oracle/ref_shim (oracle/Makefile target `ref`).
+
+TEST INFRASTRUCTURE ONLY.  /root/reference exists only in the build container: `build()` compiles when it
+is there; everywhere else the prebuilt .so (git-ignored, shipped with the snapshot) is loaded.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libsf_ref.so")
+REFERENCE_DIR = "/root/reference"
+NUM_CLUSTERS = 24
+
+
+class RefParams(C.Structure):
+    _fields_ = [("ctf_levels", C.c_int), ("max_iter_per_level", C.c_int), ("max_iter_irls", C.c_int),
+                ("use_motion_filter", C.c_int), ("k_photometric_res", C.c_float), ("irls_delta_threshold", C.c_float),
+                ("kc_cauchy", C.c_float), ("kb", C.c_float), ("kz", C.c_float), ("lambda_reg", C.c_float),
+                ("lambda_prior", C.c_float), ("previous_speed_const_weight", C.c_float),
+                ("previous_speed_eig_weight", C.c_float)]
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH) or os.path.isdir(REFERENCE_DIR)
+
+
+def build() -> str | None:
+    """Compile from the reference tree when it is present; otherwise keep whatever prebuilt library exists."""
+    if os.path.isdir(REFERENCE_DIR):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE_DIR}"])
+    return LIB_PATH if os.path.exists(LIB_PATH) else None
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if build() is None:
+            raise FileNotFoundError(LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        fp, vp = C.POINTER(C.c_float), C.c_void_p
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [C.c_int]
+        L.ref_destroy.argtypes = [vp]
+        for f in ("ref_rows", "ref_cols", "ref_default_levels", "ref_num_valid"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = C.c_int
+        L.ref_set_params.argtypes = [vp, C.POINTER(RefParams)]
+        L.ref_set_current.argtypes = [vp, fp, fp]
+        L.ref_set_prediction.argtypes = [vp, fp, fp]
+        L.ref_set_twist_old.argtypes = [vp, fp]
+        L.ref_set_T.argtypes = [vp, fp]
+        L.ref_create_image_pyramid.argtypes = [vp, C.c_int]
+        L.ref_run_solver.argtypes = [vp, C.c_int]
+        L.ref_build_segm_image.argtypes = [vp]
+        L.ref_kmeans.argtypes = [vp]
+        L.ref_warp_level.argtypes = [vp, C.c_int]
+        L.ref_linearise_level.argtypes = [vp, C.c_int, C.c_int]
+        L.ref_solve_level.argtypes = [vp]
+        L.ref_get_image.argtypes = [vp, C.c_char_p, C.c_int, fp]
+        L.ref_get_image.restype = C.c_int
+        L.ref_get_labels.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.ref_get_kmeans.argtypes = [vp, fp, C.POINTER(C.c_uint8)]
+        L.ref_get_pose.argtypes = [vp, fp, fp, fp, fp, fp]
+        L.ref_get_seg.argtypes = [vp, fp, fp, fp]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Reference:
+    """`class StaticFusion` of the reference (res_factor 1, 2, 4, 8 -> 640x480 ... 80x60), driver parameters by default."""
+
+    def __init__(self, res_factor: int = 2, **params):
+        self.L = lib()
+        self.h = self.L.ref_create(res_factor)
+        self.rows, self.cols = self.L.ref_rows(self.h), self.L.ref_cols(self.h)
+        p = dict(ctf_levels=self.L.ref_default_levels(self.h), max_iter_per_level=3, max_iter_irls=6, use_motion_filter=1,
+                 k_photometric_res=0.15, irls_delta_threshold=0.0015, kc_cauchy=0.5, kb=1.5, kz=1.5, lambda_reg=0.35,
+                 lambda_prior=0.5, previous_speed_const_weight=0.1, previous_speed_eig_weight=2.0)  # StaticFusion-datasets.cpp:79-94
+        p.update(params)
+        self.params = RefParams(**p)
+        self.L.ref_set_params(self.h, C.byref(self.params))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def set_current(self, d, i):
+        d, i = _f32(d), _f32(i)
+        self.L.ref_set_current(self.h, _fp(d), _fp(i))
+
+    def set_prediction(self, d, i):
+        d, i = _f32(d), _f32(i)
+        self.L.ref_set_prediction(self.h, _fp(d), _fp(i))
+
+    def set_twist_old(self, t):
+        t = _f32(t)
+        self.L.ref_set_twist_old(self.h, _fp(t))
+
+    def set_T(self, T):
+        T = _f32(T).reshape(16)
+        self.L.ref_set_T(self.h, _fp(T))
+
+    def create_image_pyramid(self, old_im):
+        self.L.ref_create_image_pyramid(self.h, int(old_im))
+
+    def run_solver(self, create_image_pyr=True):
+        self.L.ref_run_solver(self.h, int(create_image_pyr))
+
+    def build_segm_image(self):
+        self.L.ref_build_segm_image(self.h)
+
+    def kmeans(self):
+        self.L.ref_kmeans(self.h)
+
+    def warp_level(self, image_level):
+        self.L.ref_warp_level(self.h, image_level)
+
+    def linearise_level(self, level_i, first):
+        self.L.ref_linearise_level(self.h, level_i, int(first))
+
+    def solve_level(self):
+        self.L.ref_solve_level(self.h)
+
+    def solve_pair(self, dc, ic, dp, ip, twist_old=None):
+        """The drivers' per-frame sequence (StaticFusion-datasets.cpp:171-180)."""
+        self.set_current(dc, ic)
+        self.set_prediction(dp, ip)
+        self.set_twist_old(np.zeros(6, np.float32) if twist_old is None else twist_old)
+        self.create_image_pyramid(True)
+        self.run_solver(True)
+        self.build_segm_image()
+        return self.T()
+
+    def image(self, name, level):
+        out = np.zeros((self.rows >> level, self.cols >> level), np.float32)
+        if self.L.ref_get_image(self.h, name.encode(), level, _fp(out)) != 0:
+            raise KeyError(name)
+        return out
+
+    def labels(self, level=0):
+        out = np.zeros((self.rows >> level, self.cols >> level), np.int32)
+        self.L.ref_get_labels(self.h, level, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def kmeans_state(self):
+        cen = np.zeros((3, NUM_CLUSTERS), np.float32)
+        conn = np.zeros((NUM_CLUSTERS, NUM_CLUSTERS), np.uint8)
+        self.L.ref_get_kmeans(self.h, _fp(cen), conn.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return cen, conn
+
+    def pose(self):
+        T = np.zeros(16, np.float32)
+        a, b, c = (np.zeros(6, np.float32) for _ in range(3))
+        cov = np.zeros(36, np.float32)
+        self.L.ref_get_pose(self.h, _fp(T), _fp(a), _fp(b), _fp(c), _fp(cov))
+        return dict(T=T.reshape(4, 4), twist_odometry=a, twist_old=b, twist_level=c, est_cov=cov.reshape(6, 6))
+
+    def T(self):
+        return self.pose()["T"]
+
+    def seg(self):
+        a, b, c = (np.zeros(NUM_CLUSTERS, np.float32) for _ in range(3))
+        self.L.ref_get_seg(self.h, _fp(a), _fp(b), _fp(c))
+        return dict(b_segm=a, b_prior=b, lambda_t_w=c)
+
+    def b_perpixel(self):
+        return self.image("b_segm_perpixel", 0)
+
+    def num_valid(self):
+        return self.L.ref_num_valid(self.h)

@@ -1,8 +1,9 @@
 /*
  * sf_oracle.cpp — CPU oracle for the StaticFusion joint odometry + segmentation solver.
  *
- * TEST INFRASTRUCTURE ONLY (see sf_oracle.h).  PARITY UNPINNED: the reference has no
- * tests or golden vectors and cannot be built here; this file is a restatement of
+ * TEST INFRASTRUCTURE ONLY (see sf_oracle.h).  Pinned against the reference's own sources compiled
+ * with a header shim (oracle/ref_shim): the reference-literal policy below reproduces them bit for
+ * bit (tests/test_oracle_vs_reference.py).  This file is a restatement of
  *   FrontEnd.cpp:256-892,1071-1146   SegmentationBackground.cpp:53-197   KMeans.cpp:52-391
  * Each function cites the reference lines it follows.  Images are stored row-major here
  * but every loop keeps the reference's traversal order (u outer, v inner = Eigen
@@ -116,6 +117,41 @@ void ldlt_solve_factored(int n, const T* A, const unsigned char* zero, const T* 
         for (int k = n - 1; k > i; k--) s -= A[k * n + i] * x[k];
         x[i] = s;
     }
+}
+
+/* Gaussian elimination with partial pivoting on [A | B] (row-major n x n, n x m): the reference-literal policy's stand-in
+ * for Eigen's general `inverse()` (FrontEnd.cpp:689,755,800) and `colPivHouseholderQr().solve()` (:729,741,755). */
+template <class T>
+bool gauss_solve(int n, int m, T* A, T* B) {
+    for (int c = 0; c < n; c++) {
+        int p = c;
+        for (int r = c + 1; r < n; r++) if (std::fabs(A[r * n + c]) > std::fabs(A[p * n + c])) p = r;
+        if (A[p * n + c] == (T)0) return false;
+        if (p != c) {
+            for (int k = 0; k < n; k++) std::swap(A[p * n + k], A[c * n + k]);
+            for (int k = 0; k < m; k++) std::swap(B[p * m + k], B[c * m + k]);
+        }
+        for (int r = c + 1; r < n; r++) {
+            const T f = A[r * n + c] / A[c * n + c];
+            if (f == (T)0) continue;
+            for (int k = c; k < n; k++) A[r * n + k] -= f * A[c * n + k];
+            for (int k = 0; k < m; k++) B[r * m + k] -= f * B[c * m + k];
+        }
+    }
+    for (int k = 0; k < m; k++)
+        for (int r = n - 1; r >= 0; r--) {
+            T s = B[r * m + k];
+            for (int c = r + 1; c < n; c++) s -= A[r * n + c] * B[c * m + k];
+            B[r * m + k] = s / A[r * n + r];
+        }
+    return true;
+}
+template <class T>
+void general_inverse(int n, const T* A, T* inv) {
+    std::vector<T> M(A, A + (size_t)n * n), B((size_t)n * n, (T)0);
+    for (int i = 0; i < n; i++) B[(size_t)i * n + i] = (T)1;
+    const bool ok = gauss_solve<T>(n, n, M.data(), B.data());
+    for (int i = 0; i < n * n; i++) inv[i] = ok ? B[i] : std::numeric_limits<T>::quiet_NaN();
 }
 
 /* Cyclic Jacobi for a symmetric 6x6 (stands in for SelfAdjointEigenSolver, FrontEnd.cpp:719).
@@ -663,7 +699,7 @@ void orc_ctx::warpImagesAccurateInverse() {
     const int cols_lim = 100 * (cols_i - 1);
     const int rows_lim = 100 * (rows_i - 1);
     float T[16];
-    if (exact) rigid_inverse<double>(T_odometry, T); else rigid_inverse<float>(T_odometry, T);
+    if (exact) rigid_inverse<double>(T_odometry, T); else general_inverse<float>(4, T_odometry, T); /* :800 */
 
     auto splat = [&](int v, int u, int w, float depth_w, float intensity_w) {
         const size_t k = (size_t)v * cols_i + u;
@@ -872,25 +908,36 @@ void orc_ctx::computeSegPrior() {
 void orc_ctx::solveSegmIteration(const float* aver_res, float aver_res_overall, const double* lap) {
     const float kc = p.kc_cauchy;
     if (accum == ORC_ACCUM_F32) {
-        float A[NC * NC], rhs[NC], x[NC];
-        unsigned char zero[NC];
+        /* literal: A_seg is (24 + nc) x 24 with one (+2 lambda_reg, -2 lambda_reg) row per adjacent pair l < lc
+         * (SegmentationBackground.cpp:105-130); AtA_seg / AtB_seg are formed by sequential sums over its rows (:164-165) */
+        std::vector<std::pair<int, int>> conn;
+        for (int l = 0; l < NC; l++)
+            for (int lc = l + 1; lc < NC; lc++)
+                if (lap[l * NC + lc] != 0.0) conn.push_back(std::make_pair(l, lc));
+        const int nr = NC + (int)conn.size();
+        std::vector<float> As((size_t)nr * NC, 0.f), Bs(nr, 0.f);
+        const float weight_reg = 2.f * p.lambda_reg;
+        for (size_t q = 0; q < conn.size(); q++) { As[(NC + q) * NC + conn[q].first] = weight_reg; As[(NC + q) * NC + conn[q].second] = -weight_reg; }
         const float repr_res = std::max(0.001f, aver_res_overall);
         const float fixed_term = std::log(1.f + sq(p.kb * repr_res / (kc * aver_res_overall)));
         const float mult_res = 1.f / (kc * aver_res_overall);
-        const float wreg2 = sq(2.f * p.lambda_reg);
-        for (int i = 0; i < NC * NC; i++) A[i] = wreg2 * (float)lap[i];
         for (int l = 0; l < NC; l++) {
-            float a, b;
             if (lambda_t_w[l] > 0.1f) {
                 const float dataterm = fixed_term - std::log(1.f + sq(aver_res[l] * mult_res));
-                a = 2.f * lambda_t_w[l] * p.lambda_prior;
-                b = dataterm + 2.f * p.lambda_prior * lambda_t_w[l] * b_prior[l];
+                As[(size_t)l * NC + l] = 2.f * lambda_t_w[l] * p.lambda_prior;
+                Bs[l] = dataterm + 2.f * p.lambda_prior * lambda_t_w[l] * b_prior[l];
             } else {
-                a = 2.f * lambda_t_w[l];
-                b = 2.f * lambda_t_w[l] * b_prior[l];
+                As[(size_t)l * NC + l] = 2.f * lambda_t_w[l];
+                Bs[l] = 2.f * lambda_t_w[l] * b_prior[l];
             }
-            A[l * NC + l] += a * a;
-            rhs[l] = a * b;
+        }
+        float A[NC * NC], rhs[NC], x[NC];
+        unsigned char zero[NC];
+        for (int i = 0; i < NC; i++) {
+            for (int j = 0; j < NC; j++) { float acc = 0.f; for (int r = 0; r < nr; r++) acc += As[(size_t)r * NC + i] * As[(size_t)r * NC + j]; A[i * NC + j] = acc; }
+            float acc = 0.f;
+            for (int r = 0; r < nr; r++) acc += As[(size_t)r * NC + i] * Bs[r];
+            rhs[i] = acc;
         }
         ldlt_factor<float>(NC, A, zero);
         ldlt_solve_factored<float>(NC, A, zero, rhs, x);
@@ -1207,15 +1254,10 @@ void orc_ctx::solveOdometryAndSegmJoint() {
             for (int r = 0; r < 6; r++) est_cov[r * 6 + c] = x[r] * res_sq;
         }
     } else {
-        float F[36]; unsigned char zero[6];
+        float F[36], inv[36];
         for (int i = 0; i < 36; i++) F[i] = (float)AtA[i];
-        ldlt_factor<float>(6, F, zero);
-        for (int c = 0; c < 6; c++) {
-            float e[6] = {0, 0, 0, 0, 0, 0}, x[6];
-            e[c] = 1;
-            ldlt_solve_factored<float>(6, F, zero, e, x);
-            for (int r = 0; r < 6; r++) est_cov[r * 6 + c] = (double)(x[r] * (float)res_sq);
-        }
+        general_inverse<float>(6, F, inv);
+        for (int i = 0; i < 36; i++) est_cov[i] = (double)(inv[i] * (float)res_sq);
     }
     filterEstimateAndComputeT(Var);
 }
@@ -1268,9 +1310,50 @@ static void filterAndCompose(orc_ctx& c, float* twist) {
     se3_log<T>(Tn, lg);
     for (int i = 0; i < 6; i++) c.twist_odometry[i] = (float)lg[i];
 }
+/* reference-literal policy: float throughout, the general solves of the source (colPivHouseholderQr / inverse,
+ * FrontEnd.cpp:729,741,755) as Gaussian elimination with partial pivoting */
+static void filterAndComposeLiteral(orc_ctx& c, float* twist) {
+    float Tod[16];
+    for (int i = 0; i < 16; i++) Tod[i] = c.T_odometry[i];
+    if (c.p.use_motion_filter) {
+        float cov[36], ev[6], V[36];
+        for (int i = 0; i < 36; i++) cov[i] = (float)c.est_cov[i];
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < i; j++) { const float m = 0.5f * (cov[i * 6 + j] + cov[j * 6 + i]); cov[i * 6 + j] = m; cov[j * 6 + i] = m; }
+        jacobi_eig6<float>(cov, ev, V);  /* Bii = V */
+        float M[36], kai_b[6], kai_b_old[6], lg[6];
+        for (int i = 0; i < 36; i++) M[i] = V[i];
+        for (int i = 0; i < 6; i++) kai_b[i] = twist[i];
+        gauss_solve<float>(6, 1, M, kai_b);                         /* :729 */
+        se3_log<float>(Tod, lg);                                    /* :736-738 */
+        for (int i = 0; i < 6; i++) kai_b_old[i] = c.twist_odometry_old[i] - lg[i];
+        for (int i = 0; i < 36; i++) M[i] = V[i];
+        gauss_solve<float>(6, 1, M, kai_b_old);                     /* :741 */
+        const float e = expf(-(float)c.level);
+        const float cf = c.p.previous_speed_eig_weight * e, df = c.p.previous_speed_const_weight * e;  /* :745 */
+        float fil[6];
+        for (int i = 0; i < 6; i++) fil[i] = (kai_b[i] + (cf * ev[i] + df) * kai_b_old[i]) / (1.f + cf * ev[i] + df);  /* :750 */
+        float Vinv[36];
+        general_inverse<float>(6, V, Vinv);
+        gauss_solve<float>(6, 1, Vinv, fil);                        /* :755 twist = Bii.inverse().colPivHouseholderQr().solve(kai_b_fil) */
+        for (int i = 0; i < 6; i++) twist[i] = fil[i];
+    }
+    for (int i = 0; i < 6; i++) c.twist_level_odometry[i] = twist[i];
+    float E[16], Tn[16], lg[6];
+    se3_exp<float>(twist, E);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            float s = 0.f;
+            for (int k = 0; k < 4; k++) s += E[i * 4 + k] * Tod[k * 4 + j];
+            Tn[i * 4 + j] = s;
+        }
+    for (int i = 0; i < 16; i++) c.T_odometry[i] = Tn[i];
+    se3_log<float>(Tn, lg);
+    for (int i = 0; i < 6; i++) c.twist_odometry[i] = lg[i];
+}
 void orc_ctx::filterEstimateAndComputeT(float* twist) {
     if (accum != ORC_ACCUM_F32) filterAndCompose<double>(*this, twist);
-    else filterAndCompose<float>(*this, twist);
+    else filterAndComposeLiteral(*this, twist);
 }
 
 /* FrontEnd.cpp:1071-1146 */
@@ -1314,19 +1397,28 @@ void orc_ctx::runSolver(bool create_image_pyr, int stop_step) {
             for (int q = 0; q < 16; q++) cur_trace[62 + q] = T_odometry[q];
             cur_trace[78] = (float)status;
             /* :1130 */
-            double nrm = 0;
-            for (int q = 0; q < 6; q++) nrm += (double)twist_level_odometry[q] * (double)twist_level_odometry[q];
-            if (std::sqrt(nrm) < (double)p.outer_exit_threshold) break;
+            if (accum == ORC_ACCUM_F32) {
+                float nf = 0.f;
+                for (int q = 0; q < 6; q++) nf += twist_level_odometry[q] * twist_level_odometry[q];
+                if (std::sqrt(nf) < p.outer_exit_threshold) break;
+            } else {
+                double nrm = 0;
+                for (int q = 0; q < 6; q++) nrm += (double)twist_level_odometry[q] * (double)twist_level_odometry[q];
+                if (std::sqrt(nrm) < (double)p.outer_exit_threshold) break;
+            }
         }
     /* :1139-1144: twist_odometry_old = R^-1 * twist_odometry on each 3-half, R^-1 formed in double (MRPT) then cast */
     double R[9], Ri[9];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) R[i * 3 + j] = (double)T_odometry[i * 4 + j];
+    if (accum == ORC_ACCUM_F32) general_inverse<double>(3, R, Ri);
     const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
     const double id = 1.0 / det;
+    if (accum != ORC_ACCUM_F32) {
     Ri[0] = (R[4] * R[8] - R[5] * R[7]) * id; Ri[1] = (R[2] * R[7] - R[1] * R[8]) * id; Ri[2] = (R[1] * R[5] - R[2] * R[4]) * id;
     Ri[3] = (R[5] * R[6] - R[3] * R[8]) * id; Ri[4] = (R[0] * R[8] - R[2] * R[6]) * id; Ri[5] = (R[2] * R[3] - R[0] * R[5]) * id;
     Ri[6] = (R[3] * R[7] - R[4] * R[6]) * id; Ri[7] = (R[1] * R[6] - R[0] * R[7]) * id; Ri[8] = (R[0] * R[4] - R[1] * R[3]) * id;
+    }
     for (int h = 0; h < 2; h++)
         for (int i = 0; i < 3; i++) {
             float s = 0.f;

@@ -8,10 +8,15 @@
  *     SegmentationBackground.cpp:53-197    seg prior, 24x24 seg solve, per-pixel image
  *     KMeans.cpp:52-391                    24-means clustering, connectivity, label pyramid
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors and cannot be
- * compiled in this environment (Eigen, MRPT, OpenCV, Pangolin absent), so the
- * oracle is a restatement validated by property tests and an independent numpy
- * twin of its small dense algebra only.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN CODE: the reference ships no tests or
+ * golden vectors, but its solver sources (KMeans.cpp, SegmentationBackground.cpp,
+ * FrontEnd.cpp:256-1146, StaticFusion.h) are compiled unmodified from where they
+ * lie against a header shim (oracle/ref_shim, `make ref` -> oracle/_ref/) and the
+ * oracle's reference-literal policy (ORC_ACCUM_F32) reproduces them BIT FOR BIT,
+ * stage by stage and end to end (tests/test_oracle_vs_reference.py; fixtures
+ * generated from that build in tests/golden/reference_golden_*.npz).
+ * What is not pinned: Eigen's / MRPT's internal arithmetic (not in the reference
+ * tree, not installed): both sides use documented stand-ins for it.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product

@@ -1,8 +1,9 @@
 """Generate tests/golden/oracle_golden_*.npz with the CPU oracle (EXACT policy).
 
 The reference ships no golden vectors and cannot be built here, so these files pin the
-ORACLE's own outputs on seeded synthetic inputs: they guard the restatement against regressions and
-give the GPU parity tests fixed numbers that travel to the GPU box.  PARITY UNPINNED applies.
+ORACLE's EXACT-policy outputs on seeded synthetic inputs: they guard the CUDA numerics contract against regressions
+and give the GPU parity tests fixed numbers that travel to the GPU box.  (Reference-generated fixtures:
+make_reference_golden.py.)
 
     python tests/golden/make_golden.py
 """

@@ -1,7 +1,8 @@
 """The oracle reproduces the committed golden fixtures bit-for-bit (tests/golden/make_golden.py).
 
-PARITY UNPINNED: the fixtures are oracle outputs (the reference ships none); this pins
-the oracle against regressions and against host libm / compiler differences on another box.
+These fixtures are outputs of the oracle's EXACT policy (the CUDA contract) and guard it against regressions and
+host libm / compiler differences; the reference-generated fixtures live in reference_golden_*.npz
+(tests/test_oracle_vs_reference.py).
 """
 import glob
 import os

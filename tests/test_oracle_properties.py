@@ -1,7 +1,7 @@
 """Physical / structural properties the oracle must satisfy (the reference has no tests: SURVEY §4).
 
-PARITY UNPINNED: these tests pin the restatement to properties of the algorithm, not to
-outputs of the reference (which cannot be built here).
+These tests pin the restatement to properties of the algorithm; tests/test_oracle_vs_reference.py pins it
+to the reference's own code.
 """
 import numpy as np
 import pytest
