@@ -111,6 +111,24 @@ int sf_create_image_pyramid(sf_ctx* ctx, int old_im);
 int sf_run_solver(sf_ctx* ctx, int create_image_pyr);
 /* StaticFusion::buildSegmImage() (StaticFusion.h:177, SegmentationBackground.cpp:176). */
 int sf_build_segm_image(sf_ctx* ctx);
+/* ---- 5-frame history: completes the segmentation image exactly as the drivers produce it ---------- */
+/* Stand in for the drivers' writes to depthBuffer / intensityBuffer / odomBuffer[slot % 5] (StaticFusion.h:94-96):
+ * sf_buffer_set with explicit images (bootstrap, StaticFusion-datasets.cpp:114-116; T = NULL means identity, else
+ * column-major 4x4; depth = intensity = NULL writes odomBuffer[slot % 5] only), sf_buffer_push(im_count) with the current frame and T_odometry of the last sf_run_solver
+ * (:130-132, :182-184; device-to-device). */
+int sf_buffer_set(sf_ctx* ctx, int slot, const float* depth, const float* intensity, const float T[16], int col_major);
+int sf_buffer_push(sf_ctx* ctx, int index);
+/* StaticFusion::computeResidualsAgainstPreviousImage(int index) (StaticFusion.h:132, FrontEnd.cpp:896): call between
+ * sf_run_solver and sf_build_segm_image once im_count >= 5 (StaticFusion-datasets.cpp:175-177).  The result,
+ * perClusterAverageResidual (StaticFusion.h:93), persists in the context like the reference's member. */
+int sf_compute_residuals_against_previous_image(sf_ctx* ctx, int index);
+/* perClusterAverageResidual of every pair of the last solve: n_pairs*24 floats, NaN = no history / empty cluster. */
+int sf_get_per_cluster_average_residual(sf_ctx* ctx, float* out);
+/* Batched form: when on, sf_solve_sequence / sf_launch after sf_upload_sequence run the history stage for every pair
+ * k >= 4 of the sequence (frame k+1 against frame k-4 through the increments of pairs k-4..k) before the segmentation
+ * image is built; pairs 0..3 have no history (NaN), so callers that split a sequence overlap the pieces by 4 pairs. */
+int sf_set_history(sf_ctx* ctx, int on);
+
 /* Outputs the drivers read afterwards.  Any pointer may be NULL.
  *   T_odometry      StaticFusion.h:110 (column-major 4x4)
  *   twist_old_out   StaticFusion.h:111 after FrontEnd.cpp:1143-1144
@@ -167,6 +185,11 @@ int sf_sync(sf_ctx* ctx);
 /* Copy results of the last sf_launch back (synchronises). */
 int sf_download(sf_ctx* ctx, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
                 uint8_t* labels_u8, int out_space, int* irls_iters, int* status);
+/* Same for pairs [first_pair, first_pair + n) of the last solve (callers that overlap pieces of a sequence drop the
+ * overlap this way); per_cluster_residual: n*24 floats or NULL (always host). */
+int sf_download_range(sf_ctx* ctx, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm,
+                      float* b_perpixel, uint8_t* labels_u8, int out_space, int* irls_iters, int* status,
+                      float* per_cluster_residual);
 /* cudaStream_t of the context as an integer handle (for CUDA-event timing by the caller). */
 uint64_t sf_stream(sf_ctx* ctx);
 /* Number of kernel launches enqueued by the last sf_launch. */
@@ -189,7 +212,8 @@ int sf_get_step_stats(sf_ctx* ctx, int* n_valid, int* irls_iters);
 int sf_debug_set_stop_step(sf_ctx* ctx, int stop_step);
 /* Copy a named float plane of pair `pair` at pyramid level `image_level` to host (row-major).
  * names: depth, intensity, depth_pred, intensity_pred, depth_warped, intensity_warped,
- *        depth_inter, xx_inter, yy_inter, dcu, dcv, dct, ddu, ddv, ddt, weights_c, weights_d, null */
+ *        depth_inter, xx_inter, yy_inter, dcu, dcv, dct, ddu, ddv, ddt, weights_c, weights_d, null;
+ *        depth_warped_ref, intensity_warped_ref (level 0, after the history stage) */
 int sf_debug_get_plane(sf_ctx* ctx, const char* name, int pair, int image_level, float* out);
 /* Cluster labels of a pyramid level as int32 (24 = no depth), row-major. */
 int sf_debug_get_labels(sf_ctx* ctx, int pair, int image_level, int32_t* out);

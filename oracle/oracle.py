@@ -65,6 +65,14 @@ def lib():
         L.orc_run_solver.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_build_segm_image.argtypes = [C.c_void_p]
         L.orc_kmeans.argtypes = [C.c_void_p]
+        L.orc_buffer_set.argtypes = [C.c_void_p, C.c_int, fp, fp, fp]
+        L.orc_buffer_push.argtypes = [C.c_void_p, C.c_int]
+        L.orc_compute_residuals_against_previous_image.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_per_cluster_average_residual.argtypes = [C.c_void_p, fp]
+        L.orc_set_per_cluster_average_residual.argtypes = [C.c_void_p, fp]
+        L.orc_set_T.argtypes = [C.c_void_p, fp]
+        L.orc_get_residual_image.argtypes = [C.c_void_p, C.c_char_p, fp]
+        L.orc_get_residual_image.restype = C.c_int
         L.orc_warp_level.argtypes = [C.c_void_p, C.c_int, fp]
         L.orc_get_T.argtypes = [C.c_void_p, fp]
         L.orc_get_twists.argtypes = [C.c_void_p, fp, fp, fp]
@@ -156,6 +164,51 @@ class Oracle:
 
     def kmeans(self):
         self.L.orc_kmeans(self.h)
+
+    # ---- 5-frame history (FrontEnd.cpp:896-1069 and the drivers' ring buffers) ----
+    def buffer_set(self, slot, depth, inten, T=None):
+        d, i = _f32(depth), _f32(inten)
+        T = _f32(np.eye(4) if T is None else T).reshape(16)
+        self.L.orc_buffer_set(self.h, int(slot), _fp(d), _fp(i), _fp(T))
+
+    def buffer_push(self, index):
+        self.L.orc_buffer_push(self.h, int(index))
+
+    def compute_residuals_against_previous_image(self, index):
+        self.L.orc_compute_residuals_against_previous_image(self.h, int(index))
+
+    def per_cluster_average_residual(self):
+        out = np.zeros(NUM_CLUSTERS, np.float32)
+        self.L.orc_get_per_cluster_average_residual(self.h, _fp(out))
+        return out
+
+    def set_per_cluster_average_residual(self, v):
+        v = _f32(v)
+        self.L.orc_set_per_cluster_average_residual(self.h, _fp(v))
+
+    def set_T(self, T):
+        T = _f32(T).reshape(16)
+        self.L.orc_set_T(self.h, _fp(T))
+
+    def residual_image(self, name):
+        out = np.zeros((self.rows, self.cols), np.float32)
+        if self.L.orc_get_residual_image(self.h, name.encode(), _fp(out)) != 0:
+            raise KeyError(name)
+        return out
+
+    def track_frame(self, index, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None):
+        """One iteration of the drivers' steady-state loop (StaticFusion-datasets.cpp:171-184) with im_count = index."""
+        self.set_current(depth_cur, inten_cur)
+        self.set_prediction(depth_pred, inten_pred)
+        if twist_old is not None:
+            self.set_twist_old(twist_old)
+        self.create_image_pyramid(True)
+        self.run_solver(True)
+        if index - 5 >= 0:
+            self.compute_residuals_against_previous_image(index)
+        self.build_segm_image()
+        self.buffer_push(index)
+        return self.T()
 
     def warp_level(self, image_level, T):
         T = _f32(T).reshape(16)

@@ -106,6 +106,31 @@ void ref_set_T(void* h, const float* T_rowmajor) { StaticFusion& s = *static_cas
 void ref_create_image_pyramid(void* h, int old_im) { static_cast<StaticFusion*>(h)->createImagePyramid(old_im != 0); }
 void ref_run_solver(void* h, int create_image_pyr) { static_cast<StaticFusion*>(h)->runSolver(create_image_pyr != 0); }
 void ref_build_segm_image(void* h) { static_cast<StaticFusion*>(h)->buildSegmImage(); }
+/* the drivers' ring-buffer writes (StaticFusion-datasets.cpp:114-116, 182-184), then the reference's own method */
+void ref_buffer_set(void* h, int slot, const float* d, const float* i, const float* T_rowmajor) {
+    StaticFusion& s = *static_cast<StaticFusion*>(h);
+    const int b = ((slot % s.bufferLength) + s.bufferLength) % s.bufferLength;
+    in_rowmajor(s.depthBuffer[b], d); in_rowmajor(s.intensityBuffer[b], i);
+    Eigen::Matrix4f T; for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) T(r, c) = T_rowmajor[r * 4 + c];
+    s.odomBuffer[b] = T;
+}
+void ref_buffer_push(void* h, int index) {
+    StaticFusion& s = *static_cast<StaticFusion*>(h);
+    s.depthBuffer[index % s.bufferLength] = s.depthCurrent.replicate(1,1);
+    s.intensityBuffer[index % s.bufferLength] = s.intensityCurrent.replicate(1,1);
+    s.odomBuffer[index % s.bufferLength] = s.T_odometry;
+}
+void ref_compute_residuals_against_previous_image(void* h, int index) { static_cast<StaticFusion*>(h)->computeResidualsAgainstPreviousImage(index); }
+void ref_get_per_cluster_average_residual(void* h, float* out) { StaticFusion& s = *static_cast<StaticFusion*>(h); for (int l = 0; l < NUM_CLUSTERS; l++) out[l] = s.perClusterAverageResidual(l); }
+int ref_get_residual_image(void* h, const char* name, float* out) {
+    StaticFusion& s = *static_cast<StaticFusion*>(h);
+    const std::string n(name);
+    if (n == "depth_warped_ref") out_rowmajor(s.depthWarpedRefference, s.rows, s.cols, out);
+    else if (n == "intensity_warped_ref") out_rowmajor(s.intensityWarpedRefference, s.rows, s.cols, out);
+    else if (n == "cumulative") out_rowmajor(s.cumulativeResiduals, s.rows, s.cols, out);
+    else return -2;
+    return 0;
+}
 void ref_kmeans(void* h) { StaticFusion& s = *static_cast<StaticFusion*>(h); s.kMeans3DCoord(); s.createClustersPyramidUsingKMeans(); }
 /* one warp of pyramid level `image_level` with the current T_odometry (FrontEnd.cpp:775) */
 void ref_warp_level(void* h, int image_level) {

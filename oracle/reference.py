@@ -62,6 +62,12 @@ def lib():
         L.ref_create_image_pyramid.argtypes = [vp, C.c_int]
         L.ref_run_solver.argtypes = [vp, C.c_int]
         L.ref_build_segm_image.argtypes = [vp]
+        L.ref_buffer_set.argtypes = [vp, C.c_int, fp, fp, fp]
+        L.ref_buffer_push.argtypes = [vp, C.c_int]
+        L.ref_compute_residuals_against_previous_image.argtypes = [vp, C.c_int]
+        L.ref_get_per_cluster_average_residual.argtypes = [vp, fp]
+        L.ref_get_residual_image.argtypes = [vp, C.c_char_p, fp]
+        L.ref_get_residual_image.restype = C.c_int
         L.ref_kmeans.argtypes = [vp]
         L.ref_warp_level.argtypes = [vp, C.c_int]
         L.ref_linearise_level.argtypes = [vp, C.c_int, C.c_int]
@@ -130,6 +136,40 @@ class Reference:
 
     def kmeans(self):
         self.L.ref_kmeans(self.h)
+
+    def buffer_set(self, slot, d, i, T=None):
+        d, i = _f32(d), _f32(i)
+        T = _f32(np.eye(4) if T is None else T).reshape(16)
+        self.L.ref_buffer_set(self.h, int(slot), _fp(d), _fp(i), _fp(T))
+
+    def buffer_push(self, index):
+        self.L.ref_buffer_push(self.h, int(index))
+
+    def compute_residuals_against_previous_image(self, index):
+        self.L.ref_compute_residuals_against_previous_image(self.h, int(index))
+
+    def per_cluster_average_residual(self):
+        out = np.zeros(24, np.float32)
+        self.L.ref_get_per_cluster_average_residual(self.h, _fp(out))
+        return out
+
+    def residual_image(self, name):
+        out = np.zeros((self.rows, self.cols), np.float32)
+        if self.L.ref_get_residual_image(self.h, name.encode(), _fp(out)) != 0:
+            raise KeyError(name)
+        return out
+
+    def track_frame(self, index, d_cur, i_cur, d_pred, i_pred):
+        """One iteration of the drivers' steady-state loop (StaticFusion-datasets.cpp:171-184) with im_count = index."""
+        self.set_current(d_cur, i_cur)
+        self.set_prediction(d_pred, i_pred)
+        self.create_image_pyramid(True)
+        self.run_solver(True)
+        if index - 5 >= 0:
+            self.compute_residuals_against_previous_image(index)
+        self.build_segm_image()
+        self.buffer_push(index)
+        return self.T()
 
     def warp_level(self, image_level):
         self.L.ref_warp_level(self.h, image_level)

@@ -328,6 +328,12 @@ struct orc_ctx {
     Img b_segm_perpixel;
     float perClusterAverageResidual[NC];
 
+    /* 5-frame history (StaticFusion.h:92-99); the drivers write the ring after every frame (StaticFusion-datasets.cpp:182-184) */
+    static constexpr int bufferLength = 5;
+    Img depthBuffer[bufferLength], intensityBuffer[bufferLength];
+    float odomBuffer[bufferLength][16];
+    Img depthWarpedRefference, intensityWarpedRefference, cumulativeResiduals;
+
     float max_wc_raw, max_wd_raw;
     int status, total_irls;
     std::vector<float> trace;
@@ -351,6 +357,7 @@ struct orc_ctx {
     void filterEstimateAndComputeT(float* twist);
     void runSolver(bool create_image_pyr, int stop_step);
     void buildSegmImage();
+    void computeResidualsAgainstPreviousImage(int index);
 };
 
 void orc_ctx::init(const orc_params& pp, int accum_mode) {
@@ -383,6 +390,11 @@ void orc_ctx::init(const orc_params& pp, int accum_mode) {
         for (int k = 0; k < 3; k++) kmeans[k][l] = 0.f;
         for (int m = 0; m < NC; m++) connectivity[l][m] = (l == m);
     }
+    for (int b = 0; b < bufferLength; b++) { /* FrontEnd.cpp:96-103 (odomBuffer is left uninitialised there) */
+        depthBuffer[b].resize(rows, cols); intensityBuffer[b].resize(rows, cols);
+        for (int i = 0; i < 16; i++) odomBuffer[b][i] = (i % 5 == 0) ? 1.f : 0.f;
+    }
+    depthWarpedRefference.resize(rows, cols); intensityWarpedRefference.resize(rows, cols); cumulativeResiduals.resize(rows, cols);
     for (int i = 0; i < 16; i++) T_odometry[i] = (i % 5 == 0) ? 1.f : 0.f;
     for (int i = 0; i < 6; i++) twist_odometry[i] = twist_level_odometry[i] = twist_odometry_old[i] = 0.f;
     for (int i = 0; i < 36; i++) est_cov[i] = 0;
@@ -1439,6 +1451,157 @@ void orc_ctx::buildSegmImage() {
         }
 }
 
+/* FrontEnd.cpp:896-1069: warp the frame of five frames ago into the current view with the composed increments and
+ * average |dz| + k|dI| per cluster of the current frame.  `index` is the driver's im_count. */
+void orc_ctx::computeResidualsAgainstPreviousImage(int index) {
+    const int idx_to_warp = (index - bufferLength) % bufferLength;
+    const int trans_start = index - bufferLength + 1;
+    const bool exact = (accum != ORC_ACCUM_F32);
+    /* :901-909  T = (prod odomBuffer * T_odometry)^-1 */
+    float T[16];
+    if (!exact) {
+        float M[16], tmp[16];
+        for (int i = 0; i < 16; i++) M[i] = (i % 5 == 0) ? 1.f : 0.f;
+        auto mul = [&](const float* B) {
+            for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+                float acc = 0.f;
+                for (int k = 0; k < 4; k++) acc += M[i * 4 + k] * B[k * 4 + j];
+                tmp[i * 4 + j] = acc;
+            }
+            for (int i = 0; i < 16; i++) M[i] = tmp[i];
+        };
+        for (int i = trans_start; i < index; i++) mul(odomBuffer[i % bufferLength]);
+        mul(T_odometry);
+        general_inverse<float>(4, M, T);
+    } else { /* products in double of the float increments, one rounding, rigid inverse */
+        double M[16], tmp[16];
+        for (int i = 0; i < 16; i++) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        auto mul = [&](const float* B) {
+            for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+                double acc = 0.0;
+                for (int k = 0; k < 4; k++) acc += M[i * 4 + k] * (double)B[k * 4 + j];
+                tmp[i * 4 + j] = acc;
+            }
+            for (int i = 0; i < 16; i++) M[i] = tmp[i];
+        };
+        for (int i = trans_start; i < index; i++) mul(odomBuffer[i % bufferLength]);
+        mul(T_odometry);
+        float Mf[16];
+        for (int i = 0; i < 16; i++) Mf[i] = (float)M[i];
+        rigid_inverse<double>(Mf, T);
+    }
+
+    const float inv_f_i = 2.f * std::tan(0.5f * p.fovh) / float(cols);
+    const float disp_u_i = 0.5f * float(cols - 1);
+    const float disp_v_i = 0.5f * float(rows - 1);
+    const float f = float(cols) / (2.f * std::tan(0.5f * p.fovh));
+    const Img& dref = depthBuffer[idx_to_warp];
+    const Img& iref = intensityBuffer[idx_to_warp];
+    depthWarpedRefference.fill(0.f);
+    intensityWarpedRefference.fill(0.f);
+    Img intensity_diff = intensityCurrent;
+    const ImgI& labels_ref = clusterAllocation[0];
+    const size_t np = (size_t)rows * cols;
+    std::vector<float> wacu(np, 0.f);
+    std::vector<int64_t> dfix, ifix;
+    std::vector<int32_t> wfix;
+    if (exact) { dfix.assign(np, 0); ifix.assign(np, 0); wfix.assign(np, 0); }
+    const int cols_lim = 100 * (cols - 1);
+    const int rows_lim = 100 * (rows - 1);
+
+    auto splat = [&](int v, int u, int w, float depth_w, float intensity_w) {
+        const size_t k = (size_t)v * cols + u;
+        if (exact) {
+            dfix[k] += (int64_t)w * fixq(depth_w, 32);
+            ifix[k] += (int64_t)w * fixq(intensity_w, 22);
+            wfix[k] += w;
+        } else {
+            depthWarpedRefference.a[k] += float(w) * depth_w;
+            intensityWarpedRefference.a[k] += float(w) * intensity_w;
+            wacu[k] += float(w);
+        }
+    };
+
+    for (int j = 0; j < cols; j++)
+        for (int i = 0; i < rows; i++) {
+            const float z = dref(i, j);
+            if (z != 0.f && depthCurrent(i, j) != 0.f) { /* :951 tests the CURRENT depth at the source pixel */
+                const float intensity_w = iref(i, j);
+                const float xr = (inv_f_i * (float(j) - disp_u_i)) * z; /* :925-929 */
+                const float yr = (inv_f_i * (float(i) - disp_v_i)) * z;
+                const float x_w = T[0] * xr + T[1] * yr + T[2] * z + T[3];
+                const float y_w = T[4] * xr + T[5] * yr + T[6] * z + T[7];
+                const float depth_w = T[8] * xr + T[9] * yr + T[10] * z + T[11];
+                const float fu = 100.f * (f * x_w / depth_w + disp_u_i);
+                const float fv = 100.f * (f * y_w / depth_w + disp_v_i);
+                if (!(std::fabs(fu) < 1.0e9f) || !(std::fabs(fv) < 1.0e9f)) continue; /* see warpImagesAccurateInverse */
+                const int uwarp = int(fu);
+                const int vwarp = int(fv);
+                if ((uwarp >= 0) && (uwarp < cols_lim) && (vwarp >= 0) && (vwarp < rows_lim)) {
+                    const int uwarp_l = uwarp - uwarp % 100;
+                    const int uwarp_r = uwarp_l + 100;
+                    const int vwarp_d = vwarp - vwarp % 100;
+                    const int vwarp_u = vwarp_d + 100;
+                    const int delta_r = uwarp_r - uwarp;
+                    const int delta_l = 100 - delta_r;
+                    const int delta_u = vwarp_u - vwarp;
+                    const int delta_d = 100 - delta_u;
+                    if (std::min(delta_r, delta_l) + std::min(delta_u, delta_d) < 5) {
+                        const int ind_u = delta_r > delta_l ? uwarp_l / 100 : uwarp_r / 100;
+                        const int ind_v = delta_u > delta_d ? vwarp_d / 100 : vwarp_u / 100;
+                        splat(ind_v, ind_u, 200, depth_w, intensity_w);
+                    } else {
+                        const int v_d = vwarp_d / 100, u_l = uwarp_l / 100;
+                        const int v_u = v_d + 1, u_r = u_l + 1;
+                        splat(v_u, u_r, delta_l + delta_d, depth_w, intensity_w);
+                        splat(v_u, u_l, delta_r + delta_d, depth_w, intensity_w);
+                        splat(v_d, u_r, delta_l + delta_u, depth_w, intensity_w);
+                        splat(v_d, u_l, delta_r + delta_u, depth_w, intensity_w);
+                    }
+                }
+            } else {
+                intensity_diff(i, j) = 0.f;
+            }
+        }
+
+    /* :1025-1035 */
+    for (size_t k = 0; k < np; k++) {
+        if (exact) {
+            if (wfix[k] != 0) {
+                intensityWarpedRefference.a[k] = (float)((double)ifix[k] / ((double)wfix[k] * 4194304.0));
+                depthWarpedRefference.a[k] = (float)((double)dfix[k] / ((double)wfix[k] * 4294967296.0));
+            }
+        } else if (wacu[k] != 0.f) {
+            intensityWarpedRefference.a[k] /= wacu[k];
+            depthWarpedRefference.a[k] /= wacu[k];
+        }
+    }
+
+    /* :1039-1068 */
+    float sum_f[NC];
+    int64_t sum_q[NC];
+    int num_pix_label[NC];
+    for (int l = 0; l < NC; l++) { sum_f[l] = std::numeric_limits<float>::quiet_NaN(); sum_q[l] = 0; num_pix_label[l] = 1; }
+    for (int j = 0; j < cols; j++)
+        for (int i = 0; i < rows; i++) {
+            const float dr = depthCurrent(i, j) - depthWarpedRefference(i, j);
+            const float ir = intensity_diff(i, j) - intensityWarpedRefference(i, j);
+            const float cr = std::fabs(dr) + p.k_photometric_res * std::fabs(ir);
+            cumulativeResiduals(i, j) = cr;
+            if (depthWarpedRefference(i, j) != 0.f && depthCurrent(i, j) != 0.f) {
+                const int l = labels_ref(i, j);
+                if (exact) sum_q[l] += fixq(cr, 32);
+                else if (std::isnan(sum_f[l])) sum_f[l] = cr;
+                else sum_f[l] += cr;
+                num_pix_label[l]++;
+            }
+        }
+    for (int l = 0; l < NC; l++) {
+        if (exact) sum_f[l] = (num_pix_label[l] > 1) ? (float)fixval(sum_q[l], 32) : std::numeric_limits<float>::quiet_NaN();
+        perClusterAverageResidual[l] = sum_f[l] / float(2 * num_pix_label[l]);
+    }
+}
+
 /* =====================================================================================
  * C ABI
  * ===================================================================================== */
@@ -1493,6 +1656,30 @@ void orc_get_kmeans(const orc_ctx* c, float out[3 * NC]) {
 }
 void orc_get_connectivity(const orc_ctx* c, uint8_t out[NC * NC]) {
     for (int i = 0; i < NC; i++) for (int j = 0; j < NC; j++) out[i * NC + j] = c->connectivity[i][j] ? 1 : 0;
+}
+/* ring buffers of the drivers (StaticFusion-datasets.cpp:114-116, 182-184) */
+void orc_buffer_set(orc_ctx* c, int slot, const float* depth, const float* intensity, const float T[16]) {
+    const int b = ((slot % orc_ctx::bufferLength) + orc_ctx::bufferLength) % orc_ctx::bufferLength;
+    std::memcpy(c->depthBuffer[b].a.data(), depth, sizeof(float) * c->depthBuffer[b].a.size());
+    std::memcpy(c->intensityBuffer[b].a.data(), intensity, sizeof(float) * c->intensityBuffer[b].a.size());
+    for (int i = 0; i < 16; i++) c->odomBuffer[b][i] = T[i];
+}
+void orc_buffer_push(orc_ctx* c, int index) { /* depthCurrent, intensityCurrent, T_odometry -> slot index % 5 */
+    orc_buffer_set(c, index, c->depthCurrent.a.data(), c->intensityCurrent.a.data(), c->T_odometry);
+}
+void orc_compute_residuals_against_previous_image(orc_ctx* c, int index) { c->computeResidualsAgainstPreviousImage(index); }
+void orc_get_per_cluster_average_residual(const orc_ctx* c, float out[NC]) { for (int l = 0; l < NC; l++) out[l] = c->perClusterAverageResidual[l]; }
+void orc_set_per_cluster_average_residual(orc_ctx* c, const float in[NC]) { for (int l = 0; l < NC; l++) c->perClusterAverageResidual[l] = in[l]; }
+void orc_set_T(orc_ctx* c, const float T[16]) { for (int i = 0; i < 16; i++) c->T_odometry[i] = T[i]; }
+int orc_get_residual_image(const orc_ctx* c, const char* name, float* out) {
+    const std::string n(name);
+    const Img* src = nullptr;
+    if (n == "depth_warped_ref") src = &c->depthWarpedRefference;
+    else if (n == "intensity_warped_ref") src = &c->intensityWarpedRefference;
+    else if (n == "cumulative") src = &c->cumulativeResiduals;
+    if (!src) return -2;
+    std::memcpy(out, src->a.data(), sizeof(float) * src->a.size());
+    return 0;
 }
 int orc_get_status(const orc_ctx* c) { return c->status; }
 int orc_get_total_irls(const orc_ctx* c) { return c->total_irls; }

@@ -73,6 +73,18 @@ void orc_create_image_pyramid(orc_ctx* c, int old_im);
 void orc_run_solver(orc_ctx* c, int create_image_pyr, int stop_step);
 void orc_build_segm_image(orc_ctx* c);
 
+/* 5-frame history (StaticFusion.h:92-99; FrontEnd.cpp:896-1069).  The drivers copy the current frame and T_odometry
+ * into slot im_count % 5 after every frame (StaticFusion-datasets.cpp:114-116, 130-132, 182-184) and call
+ * computeResidualsAgainstPreviousImage(im_count) between runSolver and buildSegmImage once im_count >= 5 (:175-177). */
+void orc_buffer_set(orc_ctx* c, int slot, const float* depth, const float* intensity, const float T_rowmajor[16]);
+void orc_buffer_push(orc_ctx* c, int index);
+void orc_compute_residuals_against_previous_image(orc_ctx* c, int index);
+void orc_get_per_cluster_average_residual(const orc_ctx* c, float out[ORC_NUM_CLUSTERS]);
+void orc_set_per_cluster_average_residual(orc_ctx* c, const float in[ORC_NUM_CLUSTERS]);
+void orc_set_T(orc_ctx* c, const float T_rowmajor[16]);
+/* names: depth_warped_ref, intensity_warped_ref, cumulative (full resolution, row-major) */
+int  orc_get_residual_image(const orc_ctx* c, const char* name, float* out_rowmajor);
+
 /* stand-alone stages for unit tests */
 void orc_kmeans(orc_ctx* c); /* kMeans3DCoord + createClustersPyramidUsingKMeans on the current pyramid */
 void orc_warp_level(orc_ctx* c, int image_level, const float T_odometry_rowmajor[16]);

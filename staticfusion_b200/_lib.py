@@ -30,6 +30,8 @@ EXPORTS = [
     "sf_download", "sf_stream", "sf_last_launch_count", "sf_debug_set_stop_step", "sf_debug_get_plane",
     "sf_debug_get_labels", "sf_debug_get_kmeans", "sf_debug_get_trace", "sf_last_error", "sf_abi_version",
     "sf_profile_enable", "sf_profile_read", "sf_get_step_stats",
+    "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
+    "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -100,6 +102,12 @@ def lib():
     L.sf_launch.argtypes = [vp]
     L.sf_sync.argtypes = [vp]
     L.sf_download.argtypes = [vp, fp, fp, fp, vp, vp, C.c_int, ip, ip]
+    L.sf_download_range.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, vp, vp, C.c_int, ip, ip, fp]
+    L.sf_buffer_set.argtypes = [vp, C.c_int, fp, fp, fp, C.c_int]
+    L.sf_buffer_push.argtypes = [vp, C.c_int]
+    L.sf_compute_residuals_against_previous_image.argtypes = [vp, C.c_int]
+    L.sf_get_per_cluster_average_residual.argtypes = [vp, fp]
+    L.sf_set_history.argtypes = [vp, C.c_int]
     L.sf_stream.argtypes = [vp]
     L.sf_stream.restype = C.c_uint64
     L.sf_last_launch_count.argtypes = [vp]

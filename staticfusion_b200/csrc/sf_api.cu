@@ -37,6 +37,8 @@ struct sf_ctx {
     // current batch
     int n_pairs = 0, n_frames = 0;
     bool uploaded = false, solved = false;
+    bool is_sequence = false;  // the uploaded batch is a frame sequence (pair k = frames k, k+1)
+    int history = 0;           // sf_set_history: run the 5-frame residual stage inside sequence solves
     int stop_step = -1;
     int launches = 0;
     // drop-in trio state
@@ -52,7 +54,7 @@ struct sf_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     // the static schedule captured once per (batch shape, stop step) and replayed: removes ~500 launch gaps per solve
-    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids; cudaGraphExec_t exec; int launches; };
+    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history; cudaGraphExec_t exec; int launches; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
 };
@@ -218,6 +220,10 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
     ok = ok && alloc((void**)&a.b_perpixel, sizeof(float) * a.P0 * F);
+    ok = ok && alloc((void**)&a.pcar, sizeof(float) * NC * F);
+    ok = ok && alloc((void**)&a.ring_d, sizeof(float) * a.P0 * 5);
+    ok = ok && alloc((void**)&a.ring_i, sizeof(float) * a.P0 * 5);
+    ok = ok && alloc((void**)&a.ring_T, sizeof(float) * 16 * 5);
     ok = ok && alloc((void**)&a.stepstat, sizeof(int) * 2 * a.trace_steps * F);
     if (ok && (flags & 1)) ok = alloc((void**)&a.trace, sizeof(float) * SF_TRACE_STEP * a.trace_steps * F);
     if (!ok) {
@@ -231,6 +237,10 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.tiles, 0xff, tiles_per_pair(a.P0) * TILE_BYTES * F, c->stream);  // every label byte = invalid
     cudaMemsetAsync(a.gcount, 0, sizeof(int) * 2, c->stream);
+    cudaMemsetAsync(a.pcar, 0xff, sizeof(float) * NC * F, c->stream);  // all-ones = quiet NaN (FrontEnd.cpp:105)
+    cudaMemsetAsync(a.ring_d, 0, sizeof(float) * a.P0 * 5, c->stream);
+    cudaMemsetAsync(a.ring_i, 0, sizeof(float) * a.P0 * 5, c->stream);
+    cudaMemsetAsync(a.ring_T, 0, sizeof(float) * 16 * 5, c->stream);
     if (a.dbg) cudaMemsetAsync(a.dbg, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
@@ -247,7 +257,7 @@ void sf_destroy(sf_ctx* c) {
     Arena& a = c->a;
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.work_ctr);
-    cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel);
+    cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
     cudaFree(a.trace); cudaFree(a.stepstat);
     drop_graphs(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -308,7 +318,7 @@ int sf_upload_pairs(sf_ctx* c, int n_pairs, const float* depth_cur, const float*
     CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
     if (twist_old_in) CU(cudaStreamSynchronize(c->stream));  // caller may free twist_old_in on return
-    c->n_pairs = n_pairs; c->n_frames = 2 * n_pairs; c->uploaded = true; c->solved = false;
+    c->n_pairs = n_pairs; c->n_frames = 2 * n_pairs; c->uploaded = true; c->solved = false; c->is_sequence = false;
     return SF_OK;
 }
 
@@ -331,7 +341,7 @@ int sf_upload_sequence(sf_ctx* c, int n_frames, const float* depth, const float*
     CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
     if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
     if (twist_old_in) CU(cudaStreamSynchronize(c->stream));
-    c->n_pairs = n_pairs; c->n_frames = n_frames; c->uploaded = true; c->solved = false;
+    c->n_pairs = n_pairs; c->n_frames = n_frames; c->uploaded = true; c->solved = false; c->is_sequence = true;
     return SF_OK;
 }
 
@@ -365,7 +375,12 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
             }
             { ProfScope ps(c, 7, image_level); n += launch_pose_update(a, dp, i, k, cfg); }
         }
-    { ProfScope ps(c, 8, 0); n += launch_finish(a, dp, c->geom[0], cfg); }
+    {
+        ProfScope ps(c, 8, 0);
+        n += launch_finish(a, dp, c->geom[0], cfg);
+        if (c->history && c->is_sequence && !stop) n += launch_history(a, dp, c->geom[0], 0, 0, cfg);  // StaticFusion-datasets.cpp:175-177
+        n += launch_segm_image(a, c->geom[0], cfg);
+    }
     c->launches = n;
     CU(cudaGetLastError());
     return SF_OK;
@@ -374,7 +389,8 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
 static int launch_solve(sf_ctx* c, bool build_pyramids) {
     if (c->prof_on || !c->use_graph) return enqueue_solve(c, build_pyramids);  // per-kernel events need plain launches
     for (const auto& g : c->graphs)
-        if (g.n_pairs == c->n_pairs && g.n_frames == c->n_frames && g.stop_step == c->stop_step && g.pyramids == (int)build_pyramids) {
+        if (g.n_pairs == c->n_pairs && g.n_frames == c->n_frames && g.stop_step == c->stop_step && g.pyramids == (int)build_pyramids &&
+            g.history == (c->history && c->is_sequence)) {
             CU(cudaGraphLaunch(g.exec, c->stream));
             c->launches = g.launches;
             return SF_OK;
@@ -389,7 +405,7 @@ static int launch_solve(sf_ctx* c, bool build_pyramids) {
     const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e2 != cudaSuccess) return fail(SF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2));
-    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, exec, c->launches});
+    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, (int)(c->history && c->is_sequence), exec, c->launches});
     CU(cudaGraphLaunch(exec, c->stream));
     return SF_OK;
 }
@@ -398,9 +414,26 @@ int sf_launch(sf_ctx* c) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->uploaded) return fail(SF_E_STATE, "no batch uploaded");
     CU(cudaSetDevice(c->device));
+    // batched solves carry no history between calls: perClusterAverageResidual starts as NaN (FrontEnd.cpp:105)
+    CU(cudaMemsetAsync(c->a.pcar, 0xff, sizeof(float) * NC * c->n_pairs, c->stream));
     const int rc = launch_solve(c, true);
     if (rc == SF_OK) c->solved = true;
     return rc;
+}
+
+int sf_set_history(sf_ctx* c, int on) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    c->history = on ? 1 : 0;
+    return SF_OK;
+}
+
+int sf_get_per_cluster_average_residual(sf_ctx* c, float* out) {
+    if (!c || !out) return fail(SF_E_INVALID, "NULL argument");
+    if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->a.pcar, sizeof(float) * NC * c->n_pairs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
 }
 
 int sf_sync(sf_ctx* c) {
@@ -412,16 +445,19 @@ int sf_sync(sf_ctx* c) {
 uint64_t sf_stream(sf_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 int sf_last_launch_count(sf_ctx* c) { return c ? c->launches : 0; }
 
-int sf_download(sf_ctx* c, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel, uint8_t* labels_u8,
-                int out_space, int* irls_iters, int* status) {
+int sf_download_range(sf_ctx* c, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
+                      uint8_t* labels_u8, int out_space, int* irls_iters, int* status, float* per_cluster_residual) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    if (first_pair < 0 || n < 0 || first_pair + n > c->n_pairs) return fail(SF_E_INVALID, "pair range outside the last solve");
+    if (n == 0) return SF_OK;
     CU(cudaSetDevice(c->device));
-    const int n = c->n_pairs;
-    CU(cudaMemcpyAsync(c->h_out.data(), c->a.out, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    const Arena& a = c->a;
+    CU(cudaMemcpyAsync(c->h_out.data(), a.out + first_pair, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
     const cudaMemcpyKind kind = (out_space == SF_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, c->a.b_perpixel, sizeof(float) * c->a.P0 * n, kind, c->stream));
-    if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, c->a.P0, c->a.labels, c->a.pyr_stride, c->a.P0, (size_t)n, kind, c->stream));
+    if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, a.b_perpixel + (size_t)first_pair * a.P0, sizeof(float) * a.P0 * n, kind, c->stream));
+    if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, a.P0, a.labels + (size_t)first_pair * a.pyr_stride, a.pyr_stride, a.P0, (size_t)n, kind, c->stream));
+    if (per_cluster_residual) CU(cudaMemcpyAsync(per_cluster_residual, a.pcar + (size_t)first_pair * NC, sizeof(float) * NC * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < n; k++) {
         const PairOut& o = c->h_out[k];
@@ -434,6 +470,12 @@ int sf_download(sf_ctx* c, float* T_odometry, float* twist_old_out, float* b_seg
         if (status) status[k] = o.status;
     }
     return SF_OK;
+}
+
+int sf_download(sf_ctx* c, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel, uint8_t* labels_u8,
+                int out_space, int* irls_iters, int* status) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    return sf_download_range(c, 0, c->n_pairs, T_odometry, twist_old_out, b_segm, b_perpixel, labels_u8, out_space, irls_iters, status, nullptr);
 }
 
 int sf_solve_batch(sf_ctx* c, int n_pairs, const float* depth_cur, const float* inten_cur, const float* depth_pred,
@@ -527,7 +569,7 @@ int sf_run_solver(sf_ctx* c, int create_image_pyr) {
     CU(cudaMemcpyAsync(c->d_pred_idx, &pi, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_twist_in, c->h_twist_old, sizeof(float) * 6, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->n_pairs = 1; c->n_frames = 2; c->uploaded = true;
+    c->n_pairs = 1; c->n_frames = 2; c->uploaded = true; c->is_sequence = false;
     rc = launch_solve(c, false);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -538,7 +580,61 @@ int sf_run_solver(sf_ctx* c, int create_image_pyr) {
 int sf_build_segm_image(sf_ctx* c) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->solved) return fail(SF_E_STATE, "runSolver has not run");
-    // the per-pixel image is produced at the end of every solve (segm_image_kernel); nothing left to do
+    CU(cudaSetDevice(c->device));
+    // every solve ends with this kernel already; re-run it so that a computeResidualsAgainstPreviousImage call made
+    // in between (StaticFusion-datasets.cpp:175-180) takes effect
+    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames, nullptr};
+    launch_segm_image(c->a, c->geom[0], cfg);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_buffer_set(sf_ctx* c, int slot, const float* depth, const float* intensity, const float T[16], int col_major) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if ((depth == nullptr) != (intensity == nullptr)) return fail(SF_E_INVALID, "depth and intensity must be given together");
+    CU(cudaSetDevice(c->device));
+    const int b = ((slot % 5) + 5) % 5;
+    const size_t n = c->a.P0;
+    std::vector<float> d, i;
+    if (depth) {
+        d.resize(n); i.resize(n);
+        to_row_major(depth, d.data(), c->p.rows, c->p.cols, col_major);
+        to_row_major(intensity, i.data(), c->p.rows, c->p.cols, col_major);
+        CU(cudaMemcpyAsync(c->a.ring_d + (size_t)b * n, d.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->a.ring_i + (size_t)b * n, i.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    float Tr[16];
+    for (int r = 0; r < 4; r++)
+        for (int q = 0; q < 4; q++) Tr[r * 4 + q] = T ? T[q * 4 + r] : (r == q ? 1.f : 0.f);  // Eigen column-major -> row-major
+    CU(cudaMemcpyAsync(c->a.ring_T + 16 * b, Tr, sizeof(float) * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_buffer_push(sf_ctx* c, int index) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->solved || c->n_pairs != 1) return fail(SF_E_STATE, "sf_buffer_push follows sf_run_solver (drop-in path, one pair)");
+    CU(cudaSetDevice(c->device));
+    const int b = ((index % 5) + 5) % 5;
+    const size_t n = c->a.P0;
+    // frame slot 0 = current frame of the drop-in path; level 0 is the head of its pyramid
+    CU(cudaMemcpyAsync(c->a.ring_d + (size_t)b * n, c->a.pyr_d, sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a.ring_i + (size_t)b * n, c->a.pyr_i, sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a.ring_T + 16 * b, c->a.out[0].T, sizeof(float) * 16, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_compute_residuals_against_previous_image(sf_ctx* c, int index) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->solved || c->n_pairs != 1) return fail(SF_E_STATE, "runSolver has not run (drop-in path, one pair)");
+    if (index < 5) return fail(SF_E_INVALID, "needs im_count >= bufferLength = 5 (StaticFusion-datasets.cpp:175)");
+    CU(cudaSetDevice(c->device));
+    const LaunchCfg cfg{c->stream, 1, c->n_frames, nullptr};
+    launch_history(c->a, c->dp, c->geom[0], 1, index, cfg);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
     return SF_OK;
 }
 
@@ -625,6 +721,8 @@ int sf_debug_get_plane(sf_ctx* c, const char* name, int pair, int image_level, f
     else if (n == "intensity_pred") src = a.pyr_i + (size_t)pi * a.pyr_stride + g.off;
     else if (n == "depth_warped") src = a.warp_d + (size_t)pair * a.P0;
     else if (n == "intensity_warped") src = a.warp_i + (size_t)pair * a.P0;
+    else if (n == "depth_warped_ref" && image_level == 0) src = a.warp_d + (size_t)pair * a.P0;      // after the history stage
+    else if (n == "intensity_warped_ref" && image_level == 0) src = a.warp_i + (size_t)pair * a.P0;
     else {
         static const char* names[NPLANES] = {"depth_inter", "xx_inter", "yy_inter", "dcu", "dcv", "dct", "ddu", "ddv", "ddt", "weights_c", "weights_d"};
         for (int k = 0; k < NPLANES; k++)

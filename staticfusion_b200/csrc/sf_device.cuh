@@ -110,6 +110,12 @@ struct PairCtl {
     int it_done;       // IRLS iterations done in the current step
     int status, total_irls;
     unsigned ticket1, ticket2;
+    // ---- 5-frame history (computeResidualsAgainstPreviousImage, FrontEnd.cpp:896-1069) ----
+    float Thist[12];          // rows 0..2 of (prod odomBuffer * T_odometry)^-1
+    int hist_on;              // this pair has a 5-frame history in the current call
+    int hist_ref;             // frame index of the image to warp (into the ring or the pyramid frames)
+    long long hist_sum[NC];   // per-cluster sum of |dz| + k|dI|, 2^-32 fixed point
+    int hist_cnt[NC];
 };
 
 // ---------------------------------------------------------------------------------------------

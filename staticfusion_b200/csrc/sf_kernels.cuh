@@ -35,6 +35,10 @@ struct Arena {
     PairCtl* ctl;               // [F]
     PairOut* out;               // [F]
     float* b_perpixel;          // [F][P0]
+    float* pcar;                // [F][NC] perClusterAverageResidual (NaN until the 5-frame history ran, FrontEnd.cpp:105)
+    float* ring_d;              // [5][P0] depthBuffer     (StaticFusion.h:94), drop-in path only
+    float* ring_i;              // [5][P0] intensityBuffer
+    float* ring_T;              // [5][16] odomBuffer, row-major
     float* trace;               // [F][steps][SF_TRACE_STEP] or nullptr
     int* stepstat;              // [F][steps][2]: valid pixels, IRLS iterations
     size_t P0;                  // pixels of level 0
@@ -67,5 +71,9 @@ int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, in
 int launch_irls_pass2(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
 int launch_pose_update(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
 int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const LaunchCfg& c);
+// computeResidualsAgainstPreviousImage (FrontEnd.cpp:896-1069).  mode 0: pairs of a sequence, pair p >= 4 warps frame
+// cur_idx[p]-5 with the increments of pairs p-4..p; mode 1: pair 0 against the ring buffers with the driver's im_count = index.
+int launch_history(const Arena& a, const DevParams& p, const LevelGeom& g0, int mode, int index, const LaunchCfg& c);
+int launch_segm_image(const Arena& a, const LevelGeom& g0, const LaunchCfg& c);  // buildSegmImage
 
 }  // namespace sf

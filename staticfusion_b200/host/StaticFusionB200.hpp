@@ -9,6 +9,7 @@
 // pass `m.data()` straight through.
 #pragma once
 #include <cstdint>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -31,6 +32,7 @@ struct MatrixXf {  // column-major, like Eigen::MatrixXf
     float* data() { return a.data(); }
     const float* data() const { return a.data(); }
     void swap(MatrixXf& o) { std::swap(rows_, o.rows_); std::swap(cols_, o.cols_); a.swap(o.a); }
+    MatrixXf replicate(int, int) const { return *this; }  // the drivers copy with replicate(1,1)
 };
 struct MatrixXi {
     int rows_ = 0, cols_ = 0;
@@ -67,6 +69,11 @@ public:
     std::vector<MatrixXi> clusterAllocation;  // only level 0 is exported (what the backend consumes, Reconstruction.h:173)
     float b_segm[SF_NUM_CLUSTERS];
     MatrixXf b_segm_perpixel;
+    // ---- 5-frame history the drivers maintain (StaticFusion.h:92-96; StaticFusion-datasets.cpp:114-116, 182-184) ----
+    std::vector<MatrixXf> depthBuffer, intensityBuffer;
+    std::vector<Matrix4f> odomBuffer;
+    int bufferLength = 5;
+    float perClusterAverageResidual[SF_NUM_CLUSTERS];  // NaN until computeResidualsAgainstPreviousImage ran (FrontEnd.cpp:105)
     int irls_iterations = 0, status = 0;  // extras: SF_STATUS_* bits replace the reference's undefined behaviour
 
     // StaticFusion::StaticFusion(res_factor), FrontEnd.cpp:52-181 (solver part only)
@@ -85,6 +92,9 @@ public:
         clusterAllocation.resize(1); clusterAllocation[0].resize(rows, cols);
         for (int i = 0; i < 6; i++) twist_odometry_old[i] = 0.f;
         for (int l = 0; l < SF_NUM_CLUSTERS; l++) b_segm[l] = 0.5f;
+        depthBuffer.resize(bufferLength); intensityBuffer.resize(bufferLength); odomBuffer.resize(bufferLength);  // FrontEnd.cpp:96-103
+        for (int i = 0; i < bufferLength; i++) { depthBuffer[i].resize(rows, cols); intensityBuffer[i].resize(rows, cols); }
+        for (int l = 0; l < SF_NUM_CLUSTERS; l++) perClusterAverageResidual[l] = std::numeric_limits<float>::quiet_NaN();
         device_ = device;
     }
     ~StaticFusion() { sf_destroy(ctx_); }
@@ -105,6 +115,19 @@ public:
         check(sf_set_twist_old(ctx_, twist_odometry_old));
         check(sf_run_solver(ctx_, create_image_pyr ? 1 : 0));
         check(sf_get_outputs(ctx_, T_odometry.m, twist_odometry_old, b_segm, nullptr, nullptr, 1, &irls_iterations, &status));
+    }
+    // StaticFusion::computeResidualsAgainstPreviousImage(int index), FrontEnd.cpp:896: between runSolver and buildSegmImage
+    // once im_count >= bufferLength (StaticFusion-datasets.cpp:175-177).  The ring buffers are public members the drivers
+    // assign directly, so the slots this call reads are pushed to the device here: the image of five frames ago and the
+    // four increments in between.
+    void computeResidualsAgainstPreviousImage(int index) {
+        ensure();
+        const int idx_to_warp = (index - bufferLength) % bufferLength;
+        check(sf_buffer_set(ctx_, idx_to_warp, depthBuffer[idx_to_warp].data(), intensityBuffer[idx_to_warp].data(), odomBuffer[idx_to_warp].m, 1));
+        for (int i = index - bufferLength + 1; i < index; i++)
+            check(sf_buffer_set(ctx_, i % bufferLength, nullptr, nullptr, odomBuffer[i % bufferLength].m, 1));
+        check(sf_compute_residuals_against_previous_image(ctx_, index));
+        check(sf_get_per_cluster_average_residual(ctx_, perClusterAverageResidual));
     }
     // StaticFusion::buildSegmImage(), SegmentationBackground.cpp:176
     void buildSegmImage() {

@@ -54,12 +54,35 @@ int main(int argc, char** argv) {
         synthetic(staticFusion.depthPrediction, staticFusion.intensityPrediction, 0.f);
         synthetic(staticFusion.depthCurrent, staticFusion.intensityCurrent, 1.5f);
     }
+    int im_count = 0;
     try {
-        // bootstrap pair, StaticFusion-datasets.cpp:119-128
+        // bootstrap pair, StaticFusion-datasets.cpp:109-144
+        staticFusion.depthBuffer[im_count % staticFusion.bufferLength] = staticFusion.depthPrediction.replicate(1,1);
+        staticFusion.intensityBuffer[im_count % staticFusion.bufferLength] = staticFusion.intensityPrediction.replicate(1,1);
+        staticFusion.odomBuffer[im_count % staticFusion.bufferLength] = Matrix4f();
         staticFusion.createImagePyramid(true);
         staticFusion.kb = 1.05f;
+        im_count++;
         staticFusion.runSolver(true);
         staticFusion.buildSegmImage();
+        staticFusion.depthBuffer[im_count % staticFusion.bufferLength] = staticFusion.depthCurrent.replicate(1,1);
+        staticFusion.intensityBuffer[im_count % staticFusion.bufferLength] = staticFusion.intensityCurrent.replicate(1,1);
+        staticFusion.odomBuffer[im_count % staticFusion.bufferLength] = staticFusion.T_odometry;
+        // steady state, StaticFusion-datasets.cpp:148-184 (frame-to-frame: prediction := previous frame), synthetic input only
+        for (int k = 0; argc != 5 && k < 6; k++) {
+            staticFusion.depthPrediction.swap(staticFusion.depthCurrent);
+            staticFusion.intensityPrediction.swap(staticFusion.intensityCurrent);
+            synthetic(staticFusion.depthCurrent, staticFusion.intensityCurrent, 1.5f * (k + 2));
+            im_count++;
+            staticFusion.kb = 1.5f;
+            staticFusion.createImagePyramid(true);
+            staticFusion.runSolver(true);
+            if (im_count - staticFusion.bufferLength >= 0) staticFusion.computeResidualsAgainstPreviousImage(im_count);
+            staticFusion.buildSegmImage();
+            staticFusion.depthBuffer[im_count % staticFusion.bufferLength] = staticFusion.depthCurrent.replicate(1,1);
+            staticFusion.intensityBuffer[im_count % staticFusion.bufferLength] = staticFusion.intensityCurrent.replicate(1,1);
+            staticFusion.odomBuffer[im_count % staticFusion.bufferLength] = staticFusion.T_odometry;
+        }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 1;
@@ -70,6 +93,7 @@ int main(int argc, char** argv) {
                     staticFusion.T_odometry(r, 2), staticFusion.T_odometry(r, 3));
     double mean_b = 0;
     for (float x : staticFusion.b_segm_perpixel.a) mean_b += x;
+    std::printf("frames %d, perClusterAverageResidual[0] %.5f\n", im_count, staticFusion.perClusterAverageResidual[0]);
     std::printf("irls iterations %d, status %d, mean static weight %.4f\n", staticFusion.irls_iterations, staticFusion.status,
                 mean_b / staticFusion.b_segm_perpixel.a.size());
     return 0;

@@ -82,11 +82,15 @@ def compose_trajectory(T_colmajor: np.ndarray, start: np.ndarray | None = None) 
     return poses
 
 
-def solve_sequence_sharded(solver, depth, inten, device=None, want_images=False):
+HISTORY_HALO = 4  # computeResidualsAgainstPreviousImage looks five frames back (FrontEnd.cpp:898-909)
+
+
+def solve_sequence_sharded(solver, depth, inten, device=None, want_images=False, history=False):
     """Solve the pairs of a frame sequence owned by this rank and gather every rank's result rows.
 
     `depth` / `inten` hold the WHOLE sequence (n_frames, rows, cols) on every rank (synthetic data is
-    generated locally); only the rank's frame block is uploaded.  Returns (global table dict, local BatchResult).
+    generated locally); only the rank's frame block (plus a 4-pair halo when `history` is on) is uploaded.
+    Returns (global table dict, local BatchResult).
     """
     import torch.distributed as dist
 
@@ -94,6 +98,8 @@ def solve_sequence_sharded(solver, depth, inten, device=None, want_images=False)
     rank = dist.get_rank() if world > 1 else 0
     n_frames = int(depth.shape[0])
     f0, f1 = shard_frames(n_frames, rank, world)
-    local = solver.solve_sequence(depth[f0:f1 + 1], inten[f0:f1 + 1], want_images=want_images)
+    # with the 5-frame history every rank re-solves the last four pairs of its predecessor instead of exchanging them
+    halo = min(HISTORY_HALO, f0) if history else 0
+    local = solver.solve_sequence(depth[f0 - halo:f1 + 1], inten[f0 - halo:f1 + 1], want_images=want_images, history=history, halo=halo)
     table = gather_rows(pack_rows(local), n_frames - 1, device=device)
     return unpack_rows(table), local

@@ -49,7 +49,7 @@ def _addr(x):
 
 
 class BatchResult:
-    __slots__ = ("T", "twist_old", "b_segm", "b_perpixel", "labels", "irls_iters", "status")
+    __slots__ = ("T", "twist_old", "b_segm", "b_perpixel", "labels", "irls_iters", "status", "per_cluster_residual")
 
     def __init__(self, n, rows, cols, want_images, pinned=False):
         self.T = np.zeros((n, 16), np.float32)  # column-major 4x4 each (Eigen::Matrix4f)
@@ -66,6 +66,8 @@ class BatchResult:
                 self.labels = np.zeros((n, rows, cols), np.uint8)
         self.irls_iters = np.zeros(n, np.int32)
         self.status = np.zeros(n, np.int32)
+        # perClusterAverageResidual (StaticFusion.h:93): NaN unless the 5-frame history stage ran for the pair
+        self.per_cluster_residual = np.full((n, NUM_CLUSTERS), np.nan, np.float32)
 
     def T_matrices(self):
         """(n,4,4) row-major numpy view of the increments (T_odometry as a math matrix)."""
@@ -135,6 +137,23 @@ class StaticFusionSolver:
         self.b_segm = b
         self.irls_iterations, self.status = it.value, st.value
 
+    # 5-frame history of the drivers (StaticFusion.h:92-96, StaticFusion-datasets.cpp:114-116, 175-184)
+    def bufferSet(self, slot: int, depth, intensity, T=None):
+        """depthBuffer[slot % 5] = depth; intensityBuffer[..] = intensity; odomBuffer[..] = T (4x4 math matrix, None = identity)."""
+        d, i = (np.ascontiguousarray(x, np.float32) for x in (depth, intensity))
+        Tc = None if T is None else np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4).T).reshape(16)
+        check(self.L.sf_buffer_set(self.h, int(slot), _fp(d), _fp(i), None if Tc is None else _fp(Tc), 0))
+
+    def bufferPush(self, index: int):
+        """The drivers' three ring-buffer writes after a frame (current images and T_odometry -> slot index % 5)."""
+        check(self.L.sf_buffer_push(self.h, int(index)))
+
+    def computeResidualsAgainstPreviousImage(self, index: int):
+        check(self.L.sf_compute_residuals_against_previous_image(self.h, int(index)))
+        out = np.zeros(NUM_CLUSTERS, np.float32)
+        check(self.L.sf_get_per_cluster_average_residual(self.h, _fp(out)))
+        self.perClusterAverageResidual = out
+
     def buildSegmImage(self):
         check(self.L.sf_build_segm_image(self.h))
         bp = np.zeros((self.rows, self.cols), np.float32)
@@ -160,20 +179,36 @@ class StaticFusionSolver:
             _ip(r.irls_iters), _ip(r.status)))
         return r
 
-    def solve_sequence(self, depth, inten, twist_old=None, want_images=True) -> BatchResult:
+    def set_history(self, on: bool):
+        """Sequence solves also run computeResidualsAgainstPreviousImage for every pair with four predecessors."""
+        check(self.L.sf_set_history(self.h, int(bool(on))))
+
+    def solve_sequence(self, depth, inten, twist_old=None, want_images=True, history=False, halo=0, out=None) -> BatchResult:
+        """n frames -> n-1 pairs.  history: run the 5-frame residual stage (pairs 0..3 of the call have none);
+        halo: leading pairs that are solved only to provide that history and are dropped from the result."""
         nf = int(depth.shape[0])
         a = [_addr(x) for x in (depth, inten)]
         if a[0][1] != a[1][1]:
             raise ValueError("all image stacks must live in the same memory space")
-        r = BatchResult(nf - 1, self.rows, self.cols, want_images)
+        n = nf - 1 - halo
+        r = out if out is not None else BatchResult(n, self.rows, self.cols, want_images)
+        want_images = r.b_perpixel is not None
         tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        self.set_history(history)
+        check(self.L.sf_upload_sequence(self.h, nf, a[0][0], a[1][0], a[0][1], None if tw is None else _fp(tw)))
         self._n = nf - 1
-        check(self.L.sf_solve_sequence(
-            self.h, nf, a[0][0], a[1][0], a[0][1], None if tw is None else _fp(tw),
-            _fp(r.T), _fp(r.twist_old), _fp(r.b_segm),
-            r.b_perpixel.ctypes.data if want_images else None, r.labels.ctypes.data if want_images else None, MEM_HOST,
-            _ip(r.irls_iters), _ip(r.status)))
+        check(self.L.sf_launch(self.h))
+        self.download_range(halo, n, r)
         return r
+
+    def download_range(self, first: int, n: int, r: BatchResult, at: int = 0):
+        """Results of pairs [first, first+n) of the last solve into rows [at, at+n) of `r`."""
+        want_images = r.b_perpixel is not None
+        sl = slice(at, at + n)
+        check(self.L.sf_download_range(
+            self.h, int(first), int(n), _fp(r.T[sl]), _fp(r.twist_old[sl]), _fp(r.b_segm[sl]),
+            r.b_perpixel[sl].ctypes.data if want_images else None, r.labels[sl].ctypes.data if want_images else None, MEM_HOST,
+            _ip(r.irls_iters[sl]), _ip(r.status[sl]), _fp(r.per_cluster_residual[sl])))
 
     # ---- split phase (benchmark) ----
     def upload_pairs(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None):
@@ -269,11 +304,16 @@ class PipelinedSolver:
     so the copies are truly asynchronous.  Results are bit-identical to one big ``solve_sequence`` call.
     """
 
-    def __init__(self, params: SfParams | None = None, device: int = 0, chunk: int = 128, n_ctx: int = 3):
+    HALO = 4  # pairs a chunk re-solves so that its first pairs see their 5-frame history
+
+    def __init__(self, params: SfParams | None = None, device: int = 0, chunk: int = 128, n_ctx: int = 3, history: bool = False):
         self.params = params if params is not None else default_params()
         self.rows, self.cols = self.params.rows, self.params.cols
         self.chunk = chunk
-        self.ctx = [StaticFusionSolver(self.params, device=device, max_batch=chunk) for _ in range(n_ctx)]
+        self.history = history
+        self.ctx = [StaticFusionSolver(self.params, device=device, max_batch=chunk + (self.HALO if history else 0)) for _ in range(n_ctx)]
+        for c in self.ctx:
+            c.set_history(history)
 
     def close(self):
         for c in self.ctx:
@@ -288,19 +328,17 @@ class PipelinedSolver:
         pending = []  # (ctx, span) in flight
 
         def drain(ctx, span):
-            s0, s1 = span
-            check(L.sf_download(
-                ctx.h, _fp(r.T[s0:s1]), _fp(r.twist_old[s0:s1]), _fp(r.b_segm[s0:s1]),
-                r.b_perpixel[s0:s1].ctypes.data if want_images else None, r.labels[s0:s1].ctypes.data if want_images else None,
-                MEM_HOST, _ip(r.irls_iters[s0:s1]), _ip(r.status[s0:s1])))
+            s0, s1, halo = span
+            ctx.download_range(halo, s1 - s0, r, at=s0)
 
         for k, (s0, s1) in enumerate(spans):
             ctx = self.ctx[k % len(self.ctx)]
             if len(pending) == len(self.ctx):  # this context is still busy with an older chunk: collect it first
                 drain(*pending.pop(0))
-            ctx.upload_sequence(depth[s0:s1 + 1], inten[s0:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
+            halo = min(self.HALO, s0) if self.history else 0
+            ctx.upload_sequence(depth[s0 - halo:s1 + 1], inten[s0 - halo:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
             ctx.launch()
-            pending.append((ctx, (s0, s1)))
+            pending.append((ctx, (s0, s1, halo)))
         while pending:
             drain(*pending.pop(0))
         return r

@@ -32,3 +32,34 @@ def pose_error(Ta, Tb):
 def oracle_params_from(O, p):
     """oracle Params with the same field values as a product SfParams."""
     return O.Params(**{name: getattr(p, name) for name, _ in O.Params._fields_})
+
+
+def oracle_sequence(O, params, depth, inten, history=False, accum=None, want_images=True):
+    """The batched sequence semantics restated with the oracle: pair k = frames k, k+1 solved on its own
+    (twist_odometry_old = 0); with `history`, pair k >= 4 also runs computeResidualsAgainstPreviousImage(k+1) against
+    frame k-4 through the increments of pairs k-4..k (ring buffers filled as the drivers would have,
+    StaticFusion-datasets.cpp:182-184) before buildSegmImage.  Returns a dict of stacked outputs."""
+    accum = O.ACCUM_EXACT if accum is None else accum
+    n = depth.shape[0] - 1
+    out = dict(T=[], b_segm=[], per_cluster=[], b_perpixel=[], labels=[], irls=[], status=[])
+    Ts = []
+    for k in range(n):
+        o = O.Oracle(params, accum)
+        o.set_current(depth[k + 1], inten[k + 1])
+        o.set_prediction(depth[k], inten[k])
+        o.set_twist_old(np.zeros(6, np.float32))
+        o.create_image_pyramid(True)
+        o.run_solver(True)
+        Ts.append(o.T())
+        if history and k >= 4:
+            index = k + 1
+            o.buffer_set(index % 5, depth[k - 4], inten[k - 4])
+            for i in range(index - 4, index):
+                o.buffer_set(i % 5, depth[i], inten[i], Ts[i - 1])
+            o.compute_residuals_against_previous_image(index)
+        o.build_segm_image()
+        out["T"].append(o.T()); out["b_segm"].append(o.b_segm()); out["per_cluster"].append(o.per_cluster_average_residual())
+        out["irls"].append(o.total_irls()); out["status"].append(o.status())
+        if want_images:
+            out["b_perpixel"].append(o.b_perpixel()); out["labels"].append(o.labels(0))
+    return {k: np.stack(v) for k, v in out.items() if len(v)}

@@ -55,5 +55,26 @@ def main():
         print(name, r.rows, r.cols, "T[:3,3]", T[:3, 3])
 
 
+def history():
+    """The drivers' steady-state loop over 8 frames with the 5-frame ring buffers (StaticFusion-datasets.cpp:109-184):
+    frames 5..7 run computeResidualsAgainstPreviousImage (FrontEnd.cpp:896) before buildSegmImage."""
+    for name, scene, t0, rf in (("history_dynamic_160x120", "dynamic", 40, 4), ("history_walking_xyz_80x60", "walking_xyz", 8, 8)):
+        r = R.Reference(rf)
+        n = 9
+        d, c = synth.render_sequence(scene, n, r.rows, r.cols, start=t0)
+        r.buffer_set(0, d[0], c[0])
+        Ts, pcs, bps, wref = [], [], [], []
+        for t in range(1, n):
+            Ts.append(r.track_frame(t, d[t], c[t], d[t - 1], c[t - 1]))
+            pcs.append(r.per_cluster_average_residual())
+            bps.append(r.b_perpixel())
+        np.savez_compressed(
+            os.path.join(HERE, f"reference_{name}.npz"), depth_mm=np.round(d * 1000.0).astype(np.uint16), intensity=c,
+            res_factor=np.int32(rf), T=np.stack(Ts), per_cluster=np.stack(pcs), b_perpixel=np.stack(bps),
+            depth_warped_ref=r.residual_image("depth_warped_ref"), cumulative=r.residual_image("cumulative"))
+        print(name, "flipped clusters in last frame:", int((pcs[-1] < 0.017).sum()))
+
+
 if __name__ == "__main__":
     main()
+    history()

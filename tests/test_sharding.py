@@ -57,22 +57,23 @@ def _worker(rank, world, port, n_frames, tmpdir):
     rows, cols = 60, 80
     d, c = synth.render_sequence("dynamic", n_frames, rows, cols, start=30)
 
+    import common
+
     class OracleSolver:  # same solve_sequence contract as StaticFusionSolver
-        def solve_sequence(self, depth, inten, twist_old=None, want_images=False):
-            n = depth.shape[0] - 1
+        def solve_sequence(self, depth, inten, twist_old=None, want_images=False, history=False, halo=0):
+            n = depth.shape[0] - 1 - halo
             r = BatchResult(n, rows, cols, False)
-            for k in range(n):
-                o = O.Oracle(O.driver_params(rows, cols, ctf_levels=3), O.ACCUM_EXACT)
-                T = o.solve_pair(depth[k + 1], inten[k + 1], depth[k], inten[k])
-                r.T[k] = T.T.reshape(16)
-                r.twist_old[k] = o.twists()[1]
-                r.b_segm[k] = o.b_segm()
-                r.irls_iters[k] = o.total_irls()
-                r.status[k] = o.status()
+            o = common.oracle_sequence(O, O.driver_params(rows, cols, ctf_levels=3), depth, inten, history=history, want_images=False)
+            r.T[:] = o["T"][halo:].transpose(0, 2, 1).reshape(-1, 16)
+            r.twist_old[:] = 0
+            r.b_segm[:] = o["b_segm"][halo:]
+            r.irls_iters[:] = o["irls"][halo:]
+            r.status[:] = o["status"][halo:]
+            r.per_cluster_residual[:] = o["per_cluster"][halo:]
             return r
 
-    table, local = sharding.solve_sequence_sharded(OracleSolver(), d, c)
-    np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), **table, n_local=local.T.shape[0])
+    table, local = sharding.solve_sequence_sharded(OracleSolver(), d, c, history=True)
+    np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), **table, n_local=local.T.shape[0], per_cluster=local.per_cluster_residual)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,7 +83,7 @@ def test_two_rank_gloo_gather_equals_single_process(tmp_path):
     from oracle import oracle as O
     from staticfusion_b200 import synth
 
-    n_frames, world = 6, 2
+    n_frames, world = 12, 2
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n_frames, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(tmp_path / "rank0.npz")
@@ -98,3 +99,11 @@ def test_two_rank_gloo_gather_equals_single_process(tmp_path):
         T = o.solve_pair(d[k + 1], c[k + 1], d[k], c[k])
         assert np.array_equal(r0["T"][k], T.T.reshape(16))
         assert r0["irls_iters"][k] == o.total_irls()
+    # 5-frame history across the shard boundary: rank 1 re-solves four halo pairs, so its first pairs see the same
+    # history as in a single-process run
+    import common
+    full = common.oracle_sequence(O, O.driver_params(rows, cols, ctf_levels=3), d, c, history=True, want_images=False)
+    n0 = int(r0["n_local"])
+    assert np.array_equal(r0["per_cluster"], full["per_cluster"][:n0], equal_nan=True)
+    assert np.array_equal(r1["per_cluster"], full["per_cluster"][n0:], equal_nan=True)
+    assert np.isnan(full["per_cluster"][:4]).all() and not np.isnan(full["per_cluster"][4:]).all()
