@@ -111,6 +111,15 @@ int sf_create_image_pyramid(sf_ctx* ctx, int old_im);
 int sf_run_solver(sf_ctx* ctx, int create_image_pyr);
 /* StaticFusion::buildSegmImage() (StaticFusion.h:177, SegmentationBackground.cpp:176). */
 int sf_build_segm_image(sf_ctx* ctx);
+/* ---- depth pre-filter: the step right before the path ------------------------------------------- */
+/* Reconstruction::getFilteredDepth(cv::Mat depth, Eigen::MatrixXf& depthMat) (Reconstruction.cpp:722-732), i.e.
+ * Shaders/depth_bilateral.frag:30-76 followed by Shaders/depth_metric.frag:28-40: n_images row-major rows x cols
+ * uint16 millimetre images -> float metres (0 = invalid: outside [0.3 m, max_depth_m] before or after filtering).
+ * depth_mm / depth_out may be host or device memory (SF_MEM_*); col_major_out = 1 writes the Eigen layout (host only).
+ * max_depth_m is the reference's depthCutoff (gui default depth_max = 4.5, FrontEnd.cpp:167,174). */
+int sf_filter_depth(sf_ctx* ctx, int n_images, const uint16_t* depth_mm, int in_space, float max_depth_m, float* depth_out,
+                    int out_space, int col_major_out);
+
 /* ---- 5-frame history: completes the segmentation image exactly as the drivers produce it ---------- */
 /* Stand in for the drivers' writes to depthBuffer / intensityBuffer / odomBuffer[slot % 5] (StaticFusion.h:94-96):
  * sf_buffer_set with explicit images (bootstrap, StaticFusion-datasets.cpp:114-116; T = NULL means identity, else

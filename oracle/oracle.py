@@ -65,6 +65,9 @@ def lib():
         L.orc_run_solver.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_build_segm_image.argtypes = [C.c_void_p]
         L.orc_kmeans.argtypes = [C.c_void_p]
+        L.orc_filter_depth.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_float, C.c_int, fp]
+        L.orc_det_expf.argtypes = [C.c_float]
+        L.orc_det_expf.restype = C.c_float
         L.orc_buffer_set.argtypes = [C.c_void_p, C.c_int, fp, fp, fp]
         L.orc_buffer_push.argtypes = [C.c_void_p, C.c_int]
         L.orc_compute_residuals_against_previous_image.argtypes = [C.c_void_p, C.c_int]
@@ -106,6 +109,18 @@ def _fp(a):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def filter_depth(depth_mm, max_depth=4.5, exact=True):
+    """Reconstruction::getFilteredDepth (Reconstruction.cpp:722-732): (rows, cols) uint16 mm -> float32 m."""
+    d = np.ascontiguousarray(depth_mm, dtype=np.uint16)
+    out = np.zeros(d.shape, np.float32)
+    lib().orc_filter_depth(d.ctypes.data_as(C.POINTER(C.c_uint16)), d.shape[0], d.shape[1], float(max_depth), int(exact), _fp(out))
+    return out
+
+
+def det_expf(a):
+    return float(lib().orc_det_expf(float(a)))
 
 
 def driver_params(rows=240, cols=320, ctf_levels=None, **kw) -> Params:

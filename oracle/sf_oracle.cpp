@@ -1603,6 +1603,63 @@ void orc_ctx::computeResidualsAgainstPreviousImage(int index) {
 }
 
 /* =====================================================================================
+ * Depth pre-filter: the step right before the path
+ * ===================================================================================== */
+/* exp restated with IEEE float operations only (Cody-Waite reduction by ln2, degree-7 Horner, exact scaling), so that
+ * the CPU and CUDA evaluations agree bit for bit; < 2 ulp from expf over the range the filter uses. */
+static inline float det_expf(float a) {
+    if (!(a > -87.f)) return 0.f;
+    if (a > 0.f) a = 0.f; /* the filter's argument is -(non-negative) */
+    const float k = rintf(a * 1.44269504088896341f);
+    float r = a - k * 0.693359375f;      /* ln2 high part: 10 significant bits, k*hi is exact */
+    r = r - k * -2.12194440e-4f;         /* ln2 low part */
+    float p = 1.f / 5040.f;
+    p = p * r + 1.f / 720.f;
+    p = p * r + 1.f / 120.f;
+    p = p * r + 1.f / 24.f;
+    p = p * r + 1.f / 6.f;
+    p = p * r + 0.5f;
+    p = p * r + 1.f;
+    p = p * r + 1.f;
+    return ldexpf(p, (int)k);
+}
+
+/* Shaders/depth_bilateral.frag:30-76 followed by Shaders/depth_metric.frag:28-40, as Reconstruction::getFilteredDepth
+ * chains them (Reconstruction.cpp:722-732): 13x13 bilateral on raw u16 millimetres, invalid outside [300, maxD*1000],
+ * rounded back to u16, then metres.  Texels are addressed ideally (texture(cx/cols, cy/rows) -> texel (cx, cy)).
+ * exact == 0: libm expf (closest to what a GLSL implementation does); exact != 0: det_expf, the CUDA contract.
+ * PARITY UNPINNED for this function: the reference runs it as a GLSL fragment shader whose exp/round/texel addressing
+ * are implementation-defined and there is no GL context here; both policies are restatements of the shader text. */
+static void filter_depth(const uint16_t* in, int rows, int cols, float maxD, int exact, float* out) {
+    const float sigma_space2_inv_half = 0.024691358f;
+    const float sigma_color2_inv_half = 0.000555556f;
+    const int R = 6, D = R * 2 + 1;
+    const unsigned lim = (unsigned)(maxD * 1000.0f);
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < cols; x++) {
+            const unsigned value = in[(size_t)y * cols + x];
+            unsigned filtered = 0;
+            if (!(value > lim || value < 300u)) {
+                const int tx = std::min(x - D / 2 + D, cols);
+                const int ty = std::min(y - D / 2 + D, rows);
+                float sum1 = 0.f, sum2 = 0.f;
+                for (int cy = std::max(y - D / 2, 0); cy < ty; ++cy)
+                    for (int cx = std::max(x - D / 2, 0); cx < tx; ++cx) {
+                        const unsigned tmp = in[(size_t)cy * cols + cx];
+                        const float space2 = (float(x) - float(cx)) * (float(x) - float(cx)) + (float(y) - float(cy)) * (float(y) - float(cy));
+                        const float color2 = (float(value) - float(tmp)) * (float(value) - float(tmp));
+                        const float arg = -(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half);
+                        const float weight = exact ? det_expf(arg) : expf(arg);
+                        sum1 += float(tmp) * weight;
+                        sum2 += weight;
+                    }
+                filtered = (unsigned)roundf(sum1 / sum2);
+            }
+            out[(size_t)y * cols + x] = (filtered > lim || filtered < 300u) ? 0.f : float(filtered) / 1000.0f;
+        }
+}
+
+/* =====================================================================================
  * C ABI
  * ===================================================================================== */
 extern "C" {
@@ -1681,6 +1738,10 @@ int orc_get_residual_image(const orc_ctx* c, const char* name, float* out) {
     std::memcpy(out, src->a.data(), sizeof(float) * src->a.size());
     return 0;
 }
+void orc_filter_depth(const uint16_t* depth_mm, int rows, int cols, float max_depth_m, int exact, float* out) {
+    filter_depth(depth_mm, rows, cols, max_depth_m, exact, out);
+}
+float orc_det_expf(float a) { return det_expf(a); }
 int orc_get_status(const orc_ctx* c) { return c->status; }
 int orc_get_total_irls(const orc_ctx* c) { return c->total_irls; }
 

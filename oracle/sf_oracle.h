@@ -85,6 +85,12 @@ void orc_set_T(orc_ctx* c, const float T_rowmajor[16]);
 /* names: depth_warped_ref, intensity_warped_ref, cumulative (full resolution, row-major) */
 int  orc_get_residual_image(const orc_ctx* c, const char* name, float* out_rowmajor);
 
+/* Depth pre-filter (Shaders/depth_bilateral.frag + depth_metric.frag via Reconstruction::getFilteredDepth,
+ * Reconstruction.cpp:722-732): row-major u16 millimetres -> row-major float metres.  exact: 0 = libm expf, 1 = the
+ * reproducible exp of the CUDA contract.  Parity unpinned (GLSL on the reference side). */
+void orc_filter_depth(const uint16_t* depth_mm, int rows, int cols, float max_depth_m, int exact, float* out);
+float orc_det_expf(float a);
+
 /* stand-alone stages for unit tests */
 void orc_kmeans(orc_ctx* c); /* kMeans3DCoord + createClustersPyramidUsingKMeans on the current pyramid */
 void orc_warp_level(orc_ctx* c, int image_level, const float T_odometry_rowmajor[16]);

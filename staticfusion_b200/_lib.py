@@ -31,7 +31,7 @@ EXPORTS = [
     "sf_debug_get_labels", "sf_debug_get_kmeans", "sf_debug_get_trace", "sf_last_error", "sf_abi_version",
     "sf_profile_enable", "sf_profile_read", "sf_get_step_stats",
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
-    "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range",
+    "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -108,6 +108,7 @@ def lib():
     L.sf_compute_residuals_against_previous_image.argtypes = [vp, C.c_int]
     L.sf_get_per_cluster_average_residual.argtypes = [vp, fp]
     L.sf_set_history.argtypes = [vp, C.c_int]
+    L.sf_filter_depth.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, vp, C.c_int, C.c_int]
     L.sf_stream.argtypes = [vp]
     L.sf_stream.restype = C.c_uint64
     L.sf_last_launch_count.argtypes = [vp]

@@ -57,6 +57,10 @@ struct sf_ctx {
     struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history; cudaGraphExec_t exec; int launches; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
+    // depth pre-filter scratch (grown on demand)
+    uint16_t* d_raw = nullptr;
+    float* d_filt = nullptr;
+    size_t filt_cap = 0;
 };
 
 static void drop_graphs(sf_ctx* c) {
@@ -258,7 +262,7 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.work_ctr);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
-    cudaFree(a.trace); cudaFree(a.stepstat);
+    cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt);
     drop_graphs(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -608,6 +612,42 @@ int sf_buffer_set(sf_ctx* c, int slot, const float* depth, const float* intensit
     for (int r = 0; r < 4; r++)
         for (int q = 0; q < 4; q++) Tr[r * 4 + q] = T ? T[q * 4 + r] : (r == q ? 1.f : 0.f);  // Eigen column-major -> row-major
     CU(cudaMemcpyAsync(c->a.ring_T + 16 * b, Tr, sizeof(float) * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_filter_depth(sf_ctx* c, int n_images, const uint16_t* depth_mm, int in_space, float max_depth_m, float* depth_out, int out_space,
+                    int col_major_out) {
+    if (!c || !depth_mm || !depth_out) return fail(SF_E_INVALID, "NULL argument");
+    if (n_images < 1) return fail(SF_E_INVALID, "n_images must be >= 1");
+    if (col_major_out && out_space == SF_MEM_DEVICE) return fail(SF_E_INVALID, "column-major output is a host-side conversion");
+    CU(cudaSetDevice(c->device));
+    const size_t P = c->a.P0, n = (size_t)n_images;
+    const bool need_in = in_space != SF_MEM_DEVICE, need_out = out_space != SF_MEM_DEVICE;
+    if ((need_in || need_out) && c->filt_cap < n) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_raw); cudaFree(c->d_filt); c->d_raw = nullptr; c->d_filt = nullptr; c->filt_cap = 0;
+        CU(cudaMalloc((void**)&c->d_raw, sizeof(uint16_t) * P * n));
+        CU(cudaMalloc((void**)&c->d_filt, sizeof(float) * P * n));
+        c->filt_cap = n;
+    }
+    const uint16_t* src = depth_mm;
+    if (need_in) { CU(cudaMemcpyAsync(c->d_raw, depth_mm, sizeof(uint16_t) * P * n, cudaMemcpyHostToDevice, c->stream)); src = c->d_raw; }
+    float* dst = need_out ? c->d_filt : depth_out;
+    launch_filter_depth(src, dst, c->p.rows, c->p.cols, n_images, P, P, max_depth_m, c->stream);
+    CU(cudaGetLastError());
+    if (need_out) {
+        if (!col_major_out) CU(cudaMemcpyAsync(depth_out, c->d_filt, sizeof(float) * P * n, cudaMemcpyDeviceToHost, c->stream));
+        else {
+            std::vector<float> tmp(P * n);
+            CU(cudaMemcpyAsync(tmp.data(), c->d_filt, sizeof(float) * P * n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            const int rows = c->p.rows, cols = c->p.cols;
+            for (size_t k = 0; k < n; k++)
+                for (int v = 0; v < rows; v++)
+                    for (int u = 0; u < cols; u++) depth_out[k * P + (size_t)u * rows + v] = tmp[k * P + (size_t)v * cols + u];
+        }
+    }
     CU(cudaStreamSynchronize(c->stream));
     return SF_OK;
 }

@@ -74,6 +74,9 @@ int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const
 // computeResidualsAgainstPreviousImage (FrontEnd.cpp:896-1069).  mode 0: pairs of a sequence, pair p >= 4 warps frame
 // cur_idx[p]-5 with the increments of pairs p-4..p; mode 1: pair 0 against the ring buffers with the driver's im_count = index.
 int launch_history(const Arena& a, const DevParams& p, const LevelGeom& g0, int mode, int index, const LaunchCfg& c);
+// Reconstruction::getFilteredDepth: n images of rows x cols u16 millimetres -> float metres (strides in elements)
+int launch_filter_depth(const uint16_t* in, float* out, int rows, int cols, int n, size_t in_stride, size_t out_stride, float max_depth_m,
+                        cudaStream_t stream);
 int launch_segm_image(const Arena& a, const LevelGeom& g0, const LaunchCfg& c);  // buildSegmImage
 
 }  // namespace sf

@@ -116,6 +116,13 @@ public:
         check(sf_run_solver(ctx_, create_image_pyr ? 1 : 0));
         check(sf_get_outputs(ctx_, T_odometry.m, twist_odometry_old, b_segm, nullptr, nullptr, 1, &irls_iterations, &status));
     }
+    // Reconstruction::getFilteredDepth(cv::Mat depth, Eigen::MatrixXf& depthMat), Reconstruction.cpp:722-732: row-major u16
+    // millimetres in, column-major metres out (what cv::cv2eigen produced); max_depth = the GUI's depthCutoff
+    void getFilteredDepth(const uint16_t* depth_mm, MatrixXf& depthMat, float max_depth = 4.5f) {
+        ensure();
+        depthMat.resize(rows, cols);
+        check(sf_filter_depth(ctx_, 1, depth_mm, SF_MEM_HOST, max_depth, depthMat.data(), SF_MEM_HOST, 1));
+    }
     // StaticFusion::computeResidualsAgainstPreviousImage(int index), FrontEnd.cpp:896: between runSolver and buildSegmImage
     // once im_count >= bufferLength (StaticFusion-datasets.cpp:175-177).  The ring buffers are public members the drivers
     // assign directly, so the slots this call reads are pushed to the device here: the image of five frames ago and the

@@ -137,6 +137,23 @@ class StaticFusionSolver:
         self.b_segm = b
         self.irls_iterations, self.status = it.value, st.value
 
+    def getFilteredDepth(self, depth_mm, max_depth: float = 4.5):
+        """Reconstruction::getFilteredDepth (Reconstruction.cpp:722-732): uint16 millimetres (rows, cols) or (n, rows, cols),
+        numpy or CUDA tensor -> float32 metres of the same kind, bilateral-filtered on the device."""
+        if isinstance(depth_mm, np.ndarray):
+            src = np.ascontiguousarray(depth_mm, np.uint16)
+            out = np.zeros(src.shape, np.float32)
+            n = 1 if src.ndim == 2 else src.shape[0]
+            check(self.L.sf_filter_depth(self.h, n, src.ctypes.data, MEM_HOST, float(max_depth), out.ctypes.data, MEM_HOST, 0))
+            return out
+        import torch
+        src = depth_mm.contiguous()
+        assert src.is_cuda and src.dtype in (torch.uint16, torch.int16)
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        n = 1 if src.dim() == 2 else src.shape[0]
+        check(self.L.sf_filter_depth(self.h, n, src.data_ptr(), MEM_DEVICE, float(max_depth), out.data_ptr(), MEM_DEVICE, 0))
+        return out
+
     # 5-frame history of the drivers (StaticFusion.h:92-96, StaticFusion-datasets.cpp:114-116, 175-184)
     def bufferSet(self, slot: int, depth, intensity, T=None):
         """depthBuffer[slot % 5] = depth; intensityBuffer[..] = intensity; odomBuffer[..] = T (4x4 math matrix, None = identity)."""
