@@ -5,6 +5,7 @@
 // without any host synchronisation.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -57,6 +58,7 @@ struct sf_ctx {
     struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history; cudaGraphExec_t exec; int launches; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
+    int fused_max_tiles = 300;  // levels with at most this many 64-pixel tiles per pair run the fused IRLS kernel (SF_FUSED_MAX_TILES)
     // depth pre-filter scratch (grown on demand)
     uint16_t* d_raw = nullptr;
     float* d_filt = nullptr;
@@ -170,6 +172,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     sf_ctx* c = new (std::nothrow) sf_ctx();
     if (!c) return fail(SF_E_NOMEM, "host allocation failed");
     c->p = *p; c->device = device; c->max_batch = max_batch; c->flags = flags; c->levels = p->ctf_levels;
+    if (const char* e = std::getenv("SF_FUSED_MAX_TILES")) c->fused_max_tiles = std::atoi(e);  // tuning / A-B measurements
     fill_dev_params(c);
     // level geometry, constants evaluated exactly as the reference does (FrontEnd.cpp:378-380, 537, 778-780, 874)
     size_t off = 0;
@@ -373,10 +376,14 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
             else n += launch_step_begin(a, i, k, cfg);
             { ProfScope ps(c, 4, image_level); n += launch_linearise(a, dp, g, first, cfg); n += launch_step_prep(a, dp, i, k, cfg); }
             if (i * c->p.max_iter_per_level + k == c->stop_step) { stop = true; break; }
-            for (int it = 1; it <= c->p.max_iter_irls; it++) {
-                { ProfScope ps(c, 5, image_level); n += launch_irls_pass1(a, dp, g, i, k, it, cfg); }
-                { ProfScope ps(c, 6, image_level); n += launch_irls_pass2(a, dp, g, i, k, it, cfg); }
-            }
+            if ((int)tiles_per_pair((size_t)g.P) <= c->fused_max_tiles) {  // small level: one block runs the pair's whole IRLS loop
+                ProfScope ps(c, 5, image_level);
+                n += launch_irls_fused(a, dp, g, i, k, cfg);
+            } else
+                for (int it = 1; it <= c->p.max_iter_irls; it++) {
+                    { ProfScope ps(c, 5, image_level); n += launch_irls_pass1(a, dp, g, i, k, it, cfg); }
+                    { ProfScope ps(c, 6, image_level); n += launch_irls_pass2(a, dp, g, i, k, it, cfg); }
+                }
             { ProfScope ps(c, 7, image_level); n += launch_pose_update(a, dp, i, k, cfg); }
         }
     {

@@ -122,7 +122,9 @@ struct PairCtl {
 // fixed point helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long fixq(float x, int s) { return __float2ll_rn(ldexpf(x, s)); }
-__device__ __forceinline__ double fixval(long long acc, int s) { return ldexp((double)acc, -s); }
+// x * 2^e for |e| <= 1022 and no over/underflow of the result: identical to ldexp, without its slow path
+__device__ __forceinline__ double scale_pow2(double x, int e) { return x * __hiloint2double((1023 + e) << 20, 0); }
+__device__ __forceinline__ double fixval(long long acc, int s) { return scale_pow2((double)acc, -s); }
 __host__ __device__ __forceinline__ int scale_exponent(float bound) {
     if (!(bound > 0.f) || !isfinite(bound)) return 0;
     int e;
@@ -136,38 +138,45 @@ __host__ __device__ __forceinline__ int scale_exponent(float bound) {
 // ---------------------------------------------------------------------------------------------
 // small dense algebra in double — same operation sequences as the oracle's templates
 // ---------------------------------------------------------------------------------------------
+// (all loops fully unrolled: with N = 6 every index is a compile-time constant and the arrays live in registers)
 template <int N>
-__device__ inline int ldlt_factor(double* A, unsigned char* zero) {
+__device__ __forceinline__ int ldlt_factor(double* A, unsigned char* zero) {
     const double tiny = 1e-20;
     int nz = 0;
+#pragma unroll
     for (int j = 0; j < N; j++) {
         double d = A[j * N + j];
+#pragma unroll
         for (int k = 0; k < j; k++) d -= (A[j * N + k] * A[j * N + k]) * A[k * N + k];
         A[j * N + j] = d;
-        if (!(d > tiny)) {
-            zero[j] = 1; nz++;
-            for (int i = j + 1; i < N; i++) A[i * N + j] = 0.0;
-            continue;
-        }
-        zero[j] = 0;
+        const bool z = !(d > tiny);
+        zero[j] = z ? 1 : 0;
+        nz += z ? 1 : 0;
+#pragma unroll
         for (int i = j + 1; i < N; i++) {
             double s = A[i * N + j];
+#pragma unroll
             for (int k = 0; k < j; k++) s -= (A[i * N + k] * A[j * N + k]) * A[k * N + k];
-            A[i * N + j] = s / d;
+            A[i * N + j] = z ? 0.0 : s / d;
         }
     }
     return nz;
 }
 template <int N>
-__device__ inline void ldlt_solve_factored(const double* A, const unsigned char* zero, const double* b, double* x) {
+__device__ __forceinline__ void ldlt_solve_factored(const double* A, const unsigned char* zero, const double* b, double* x) {
+#pragma unroll
     for (int i = 0; i < N; i++) {
         double s = b[i];
+#pragma unroll
         for (int k = 0; k < i; k++) s -= A[i * N + k] * x[k];
         x[i] = s;
     }
+#pragma unroll
     for (int i = 0; i < N; i++) x[i] = zero[i] ? 0.0 : x[i] / A[i * N + i];
+#pragma unroll
     for (int i = N - 1; i >= 0; i--) {  // descending k, as in the oracle
         double s = x[i];
+#pragma unroll
         for (int k = N - 1; k > i; k--) s -= A[k * N + i] * x[k];
         x[i] = s;
     }
@@ -178,17 +187,24 @@ __device__ inline void ldlt_solve_factored(const double* A, const unsigned char*
 // serial ldlt_factor above, so the result is bit-identical to it.
 template <int LD>
 __device__ inline void ldlt24_warp(double* A, double* rhs, double* x, unsigned char* zero, int lane) {
+    // Right-looking form: once column k is final, every remaining element (i, j > k) of the lower triangle gets its
+    // k-th term subtracted -- independent updates instead of one dependent chain per element, and the same sequence
+    // s -= (L[i][k] * L[j][k]) * D[k], k ascending, as the serial code sees.
     const double tiny = 1e-20;
-    for (int j = 0; j < NC; j++) {
-        double d = A[j * LD + j];
-        for (int k = 0; k < j; k++) d -= (A[j * LD + k] * A[j * LD + k]) * A[k * LD + k];
+    __syncwarp();
+    for (int k = 0; k < NC; k++) {
+        const double d = A[k * LD + k];  // final: all terms k' < k have been subtracted
         const bool z = !(d > tiny);
+        if (lane == 0) zero[k] = z ? 1 : 0;
+        double lik = 0.0;
+        if (lane > k && lane < NC) {
+            lik = z ? 0.0 : A[lane * LD + k] / d;
+            A[lane * LD + k] = lik;
+        }
         __syncwarp();
-        if (lane == 0) { A[j * LD + j] = d; zero[j] = z ? 1 : 0; }
-        if (lane > j && lane < NC) {
-            double s = A[lane * LD + j];
-            for (int k = 0; k < j; k++) s -= (A[lane * LD + k] * A[j * LD + k]) * A[k * LD + k];
-            A[lane * LD + j] = z ? 0.0 : s / d;
+        if (lane > k && lane < NC) {
+#pragma unroll 4
+            for (int j = k + 1; j <= lane; j++) A[lane * LD + j] -= (lik * A[j * LD + k]) * d;
         }
         __syncwarp();
     }

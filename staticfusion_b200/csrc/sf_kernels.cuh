@@ -69,6 +69,7 @@ int launch_linearise(const Arena& a, const DevParams& p, const LevelGeom& g, int
 int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
 int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
 int launch_irls_pass2(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
+int launch_irls_fused(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, const LaunchCfg& c);
 int launch_pose_update(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
 int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const LaunchCfg& c);
 // computeResidualsAgainstPreviousImage (FrontEnd.cpp:896-1069).  mode 0: pairs of a sequence, pair p >= 4 warps frame
