@@ -331,10 +331,13 @@ def main():
     device_step(); s.sync()  # one profiled warm step so the event pool exists
     prof_ms = np.zeros((sf._lib.PROF_CLASSES, sf._lib.PROF_LEVELS))
     prof_n = np.zeros_like(prof_ms)
+    pass1_fine_ms = []  # per step: the event time of every finest-level irls_pass1 launch, in launch order
     for _ in range(a.steps):
         device_step()
         ms, cnt = s.profile_read()  # waits for the step; events only, no extra kernels
         prof_ms += ms; prof_n += cnt
+        rc, rl, rms = s.profile_records()
+        pass1_fine_ms.append(rms[(rc == 5) & (rl == 0)].astype(np.float64))
     s.profile_enable(False)
 
     # --- e2e: public API, pinned HOST buffers in, results out, every step.  The batch is a sequence of F+1 frames
@@ -385,14 +388,49 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bytes_pass1 / (ms_pass1 * 1e-3) / 1e9 if ms_pass1 > 0 else 0.0
         n_l0_launches = int(prof_n[5, 0])
+        # The static schedule enqueues max_iter_per_level x max_iter_irls launches of the kernel per step; a launch whose
+        # pairs have all left the IRLS loop returns after one load.  Launch (k, it) streams the pairs with it_done >= it at
+        # step (finest level, k): 48 B per valid pixel of those pairs.
+        per_launch = []
+        n_sched = len(steps_fine) * p.max_iter_irls
+        if all(len(x) == n_sched for x in pass1_fine_ms):
+            lm = np.stack(pass1_fine_ms).sum(axis=0)  # ms per scheduled launch, summed over the K steps
+            for j in range(n_sched):
+                st, itn = steps_fine[j // p.max_iter_irls], j % p.max_iter_irls + 1
+                act = it[:, st] >= itn
+                per_launch.append({"outer": j // p.max_iter_irls, "irls_it": itn, "active_pairs": int(act.sum()),
+                                   "bytes": 48.0 * float(nv[act, st].sum()), "ms": float(lm[j]) / a.steps})
+        work = [x for x in per_launch if x["bytes"] > 0]
+        if work:
+            w_bytes = sum(x["bytes"] for x in work); w_ms = sum(x["ms"] for x in work)
+            achieved = w_bytes / (w_ms * 1e-3) / 1e9
+            full = max(work, key=lambda x: x["bytes"])
+            detail = {"launches_with_work_per_step": len(work), "algorithmic_bytes_per_launch": w_bytes / len(work),
+                      "avg_launch_ms": w_ms / len(work),
+                      "fullest_launch": {**full, "achieved": full["bytes"] / (full["ms"] * 1e-3) / 1e9,
+                                         "frac": full["bytes"] / (full["ms"] * 1e-3) / 1e9 / peak},
+                      "empty_launches_per_step": len(per_launch) - len(work),
+                      "empty_launch_ms_per_step": sum(x["ms"] for x in per_launch if x["bytes"] == 0),
+                      "all_scheduled_launches": {"achieved": bytes_pass1 / (ms_pass1 * 1e-3) / 1e9 if ms_pass1 > 0 else 0.0,
+                                                 "launches": n_l0_launches, "avg_launch_ms": ms_pass1 / max(n_l0_launches, 1)},
+                      "per_launch": [x for x in per_launch if x["bytes"] > 0]}
+        else:
+            achieved = bytes_pass1 / (ms_pass1 * 1e-3) / 1e9 if ms_pass1 > 0 else 0.0
+            detail = {"algorithmic_bytes_per_launch": bytes_pass1 / max(n_l0_launches, 1), "launches": n_l0_launches,
+                      "avg_launch_ms": ms_pass1 / max(n_l0_launches, 1)}
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one full launch, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json")))
+            if tj.get("config") == a.config:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         roof = {"bound": "hbm", "kernel": "irls_pass1_kernel (finest level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "timing": "CUDA events around every launch of the kernel on the library's stream, same K steps re-run with plain launches",
-                "frac": achieved / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": bytes_pass1 / max(n_l0_launches, 1), "launches": n_l0_launches,
-                "avg_launch_ms": ms_pass1 / max(n_l0_launches, 1)}
+                "timing": "CUDA events around every launch of the kernel on the library's stream (same K steps re-run with plain launches); "
+                          "achieved = algorithmic bytes / event time summed over the launches that had pairs to stream",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)", **detail}
         names = sf._lib.PROF_NAMES
         kern = {f"{names[k]}_L{l}": round(float(prof_ms[k, l]) / a.steps, 4) for k in range(prof_ms.shape[0]) for l in range(prof_ms.shape[1])
                 if prof_n[k, l] > 0}

@@ -212,6 +212,9 @@ int sf_profile_enable(sf_ctx* ctx, int on);
 /* After sf_sync: summed device time [ms] and launch counts per (class, pyramid level) of the last sf_launch;
  * both arrays hold SF_PROF_CLASSES*SF_PROF_LEVELS entries, index class*SF_PROF_LEVELS + image_level. */
 int sf_profile_read(sf_ctx* ctx, float* ms, int* launches);
+/* The same event pairs one by one, in launch order: up to `capacity` records of (class, image level, milliseconds);
+ * *n_records receives the number of records of the last sf_launch (may exceed capacity). */
+int sf_profile_read_records(sf_ctx* ctx, int capacity, int* cls, int* level, float* ms, int* n_records);
 /* Per pair and step (ctf_levels*max_iter_per_level steps, index level*max_iter_per_level + k) of the last solve:
  * valid pixels N (0 = step not executed) and IRLS iterations run.  Arrays hold n_pairs*steps ints. */
 int sf_get_step_stats(sf_ctx* ctx, int* n_valid, int* irls_iters);

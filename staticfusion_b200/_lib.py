@@ -29,7 +29,7 @@ EXPORTS = [
     "sf_solve_batch", "sf_solve_sequence", "sf_upload_pairs", "sf_upload_sequence", "sf_launch", "sf_sync",
     "sf_download", "sf_stream", "sf_last_launch_count", "sf_debug_set_stop_step", "sf_debug_get_plane",
     "sf_debug_get_labels", "sf_debug_get_kmeans", "sf_debug_get_trace", "sf_last_error", "sf_abi_version",
-    "sf_profile_enable", "sf_profile_read", "sf_get_step_stats",
+    "sf_profile_enable", "sf_profile_read", "sf_profile_read_records", "sf_get_step_stats",
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
     "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
 ]
@@ -119,6 +119,7 @@ def lib():
     L.sf_debug_get_trace.argtypes = [vp, C.c_int, fp, C.c_int]
     L.sf_profile_enable.argtypes = [vp, C.c_int]
     L.sf_profile_read.argtypes = [vp, fp, ip]
+    L.sf_profile_read_records.argtypes = [vp, C.c_int, ip, ip, fp, ip]
     L.sf_get_step_stats.argtypes = [vp, ip, ip]
     L.sf_last_error.restype = C.c_char_p
     L.sf_abi_version.restype = C.c_int

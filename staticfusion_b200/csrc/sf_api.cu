@@ -34,6 +34,7 @@ struct sf_ctx {
     int* d_cur_idx = nullptr;
     int* d_pred_idx = nullptr;
     float* d_twist_in = nullptr;
+    uint8_t* d_seed_map = nullptr;
     int n_frames_cap = 0;
     // current batch
     int n_pairs = 0, n_frames = 0;
@@ -216,12 +217,14 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&c->d_pred_idx, sizeof(int) * F);
     ok = ok && alloc((void**)&c->d_twist_in, sizeof(float) * 6 * F);
     ok = ok && alloc((void**)&a.labels, a.pyr_stride * F);
+    if (c->levels > 1) ok = ok && alloc((void**)&c->d_seed_map, (size_t)c->geom[1].P);
     ok = ok && alloc((void**)&a.acc_d, sizeof(long long) * a.P0 * F);
     ok = ok && alloc((void**)&a.acc_iw, sizeof(unsigned long long) * a.P0 * F);
     ok = ok && alloc((void**)&a.warp_d, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.tiles, tiles_per_pair(a.P0) * TILE_BYTES * F);
     ok = ok && alloc((void**)&a.gcount, sizeof(int) * 2);
+    ok = ok && alloc((void**)&a.active_list, sizeof(int) * F);
     ok = ok && alloc((void**)&a.work_ctr, sizeof(int) * MAX_WORK_CTRS);
     if (ok && (flags & 1)) ok = alloc((void**)&a.dbg, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
@@ -239,6 +242,24 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
         return fail(SF_E_NOMEM, msg);
     }
     a.cur_idx = c->d_cur_idx; a.pred_idx = c->d_pred_idx;
+    if (c->levels > 1) {  // seed labelling of level 1, KMeans.cpp:87-101 (integer arithmetic; 24 = no seed within range)
+        const LevelGeom& g1 = c->geom[1];
+        std::vector<uint8_t> seed((size_t)g1.P);
+        for (int v = 0; v < g1.rows; v++)
+            for (int u = 0; u < g1.cols; u++) {
+                unsigned min_dist = 1000000u;
+                int lab = NC;
+                for (int l = 0; l < NC; l++) {
+                    const int dv = v - (int)c->dp.km_v_label[l], du = u - (int)c->dp.km_u_label[l];
+                    const unsigned qd = (unsigned)(dv * dv + du * du);
+                    if (qd < min_dist) { lab = l; min_dist = qd; }
+                }
+                seed[(size_t)v * g1.cols + u] = (uint8_t)lab;
+            }
+        cudaMemcpyAsync(c->d_seed_map, seed.data(), seed.size(), cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);  // the staging vector goes out of scope
+        a.seed_map = c->d_seed_map;
+    }
     // splat accumulators are kept zero between uses (warp_normalise clears what it reads)
     cudaMemsetAsync(a.acc_d, 0, sizeof(long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
@@ -262,8 +283,8 @@ void sf_destroy(sf_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Arena& a = c->a;
-    cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in);
-    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.work_ctr);
+    cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in); cudaFree(c->d_seed_map);
+    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.active_list); cudaFree(a.work_ctr);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
     cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt);
     drop_graphs(c);
@@ -725,6 +746,19 @@ int sf_profile_read(sf_ctx* c, float* ms, int* launches) {
         CU(cudaEventElapsedTime(&t, r.e0, r.e1));
         ms[r.cls * SF_PROF_LEVELS + r.level] += t;
         launches[r.cls * SF_PROF_LEVELS + r.level] += 1;
+    }
+    return SF_OK;
+}
+
+int sf_profile_read_records(sf_ctx* c, int capacity, int* cls, int* level, float* ms, int* n_records) {
+    if (!c || !cls || !level || !ms || !n_records || capacity < 0) return fail(SF_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    *n_records = (int)c->prof.size();
+    for (int i = 0; i < (int)c->prof.size() && i < capacity; i++) {
+        const auto& r = c->prof[i];
+        CU(cudaEventElapsedTime(&ms[i], r.e0, r.e1));
+        cls[i] = r.cls; level[i] = r.level;
     }
     return SF_OK;
 }

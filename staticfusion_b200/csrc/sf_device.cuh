@@ -121,7 +121,9 @@ struct PairCtl {
 // ---------------------------------------------------------------------------------------------
 // fixed point helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long fixq(float x, int s) { return __float2ll_rn(ldexpf(x, s)); }
+// round(x * 2^s): the multiplication by a power of two is exact (no overflow for the value ranges of the sums, gradual
+// underflow is exact as well), so this equals llrint(ldexp(x, s)) of the oracle without ldexpf's special-case code
+__device__ __forceinline__ long long fixq(float x, int s) { return __float2ll_rn(x * __int_as_float((127 + s) << 23)); }
 // x * 2^e for |e| <= 1022 and no over/underflow of the result: identical to ldexp, without its slow path
 __device__ __forceinline__ double scale_pow2(double x, int e) { return x * __hiloint2double((1023 + e) << 20, 0); }
 __device__ __forceinline__ double fixval(long long acc, int s) { return scale_pow2((double)acc, -s); }

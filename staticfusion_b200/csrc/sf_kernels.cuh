@@ -24,6 +24,7 @@ struct Arena {
     const int* pred_idx;
     // per pair
     uint8_t* labels;            // [F][pyr_stride] cluster labels, 24 = no depth
+    const uint8_t* seed_map;    // [P1] nearest k-means seed of every level-1 pixel (KMeans.cpp:87-101): a function of the image size only
     long long* acc_d;           // [F][P0] warp depth accumulator (fixed point 2^32)
     unsigned long long* acc_iw; // [F][P0] packed: weight sum (high 22 bits) | intensity sum (low 42 bits, 2^22)
     float* warp_d;              // [F][P0]
@@ -31,6 +32,7 @@ struct Arena {
     uint8_t* tiles;             // [F][tiles_per_pair(P0)][TILE_BYTES] raw Jacobian rows + valid-pixel labels
     float* dbg;                 // [F][NPLANES][P0] linearisation planes, only with the trace flag (else nullptr)
     int* gcount;                // [2]: pairs active in the current step, pairs still inside the IRLS loop
+    int* active_list;           // [F] indices of the pairs active in the current step (first gcount[0] entries)
     int* work_ctr;              // [MAX_WORK_CTRS] dynamic item counters, one per pass launch of a solve (zeroed by init_pairs)
     PairCtl* ctl;               // [F]
     PairOut* out;               // [F]

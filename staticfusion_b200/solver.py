@@ -276,6 +276,15 @@ class StaticFusionSolver:
         check(self.L.sf_profile_read(self.h, _fp(ms), _ip(cnt)))
         return ms.reshape(_lib.PROF_CLASSES, _lib.PROF_LEVELS), cnt.reshape(_lib.PROF_CLASSES, _lib.PROF_LEVELS)
 
+    def profile_records(self):
+        """(class, level, ms) arrays, one entry per event pair of the last launch in launch order (call after sync)."""
+        cap = 4096
+        cls = np.zeros(cap, np.int32); lvl = np.zeros(cap, np.int32); ms = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        check(self.L.sf_profile_read_records(self.h, cap, _ip(cls), _ip(lvl), _fp(ms), C.byref(n)))
+        k = min(n.value, cap)
+        return cls[:k], lvl[:k], ms[:k]
+
     def step_stats(self):
         """(n_valid, irls_iters) int arrays of shape (n_pairs, steps) for the last solve."""
         steps = self.params.ctf_levels * self.params.max_iter_per_level
