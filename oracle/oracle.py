@@ -66,6 +66,10 @@ def lib():
         L.orc_build_segm_image.argtypes = [C.c_void_p]
         L.orc_kmeans.argtypes = [C.c_void_p]
         L.orc_filter_depth.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_float, C.c_int, fp]
+        L.orc_convert_frame.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, fp, fp,
+                                        C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)]
+        L.orc_pose_compose.argtypes = [fp, fp, fp]
+        L.orc_quat_from_rotation.argtypes = [fp, fp]
         L.orc_det_expf.argtypes = [C.c_float]
         L.orc_det_expf.restype = C.c_float
         L.orc_buffer_set.argtypes = [C.c_void_p, C.c_int, fp, fp, fp]
@@ -117,6 +121,36 @@ def filter_depth(depth_mm, max_depth=4.5, exact=True):
     out = np.zeros(d.shape, np.float32)
     lib().orc_filter_depth(d.ctypes.data_as(C.POINTER(C.c_uint16)), d.shape[0], d.shape[1], float(max_depth), int(exact), _fp(out))
     return out
+
+
+def convert_frame(bgr, depth_raw, res_factor=2):
+    """StaticFusion::loadImageFromSequenceAssoc (FrontEnd.cpp:216-254), conversion half: decoded BGR u8 (H, W, 3) and
+    u16 depth (H, W) -> (intensity f32, depth f32 metres, depth_mm u16, color u8 x3), each (H/rf, W/rf), flipped."""
+    b = np.ascontiguousarray(bgr, dtype=np.uint8)
+    d = np.ascontiguousarray(depth_raw, dtype=np.uint16)
+    H, W = d.shape
+    h, w = H // res_factor, W // res_factor
+    inten = np.zeros((h, w), np.float32); dep = np.zeros((h, w), np.float32)
+    mm = np.zeros((h, w), np.uint16); col = np.zeros((h, w, 3), np.uint8)
+    lib().orc_convert_frame(b.ctypes.data_as(C.POINTER(C.c_uint8)), d.ctypes.data_as(C.POINTER(C.c_uint16)), H, W, int(res_factor),
+                            _fp(inten), _fp(dep), mm.ctypes.data_as(C.POINTER(C.c_uint16)), col.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return inten, dep, mm, col
+
+
+def pose_compose(A, B):
+    """currPose * T_odometry in float (Reconstruction.cpp:256,265); row-major 4x4."""
+    a, b = _f32(A), _f32(B)
+    out = np.zeros((4, 4), np.float32)
+    lib().orc_pose_compose(_fp(a), _fp(b), _fp(out))
+    return out
+
+
+def quat_from_rotation(T):
+    """Eigen::Quaternionf(rotation part of T) as (x, y, z, w) (Datasets.cpp:259, Reconstruction.cpp:480)."""
+    t = _f32(T)
+    q = np.zeros(4, np.float32)
+    lib().orc_quat_from_rotation(_fp(t), _fp(q))
+    return q
 
 
 def det_expf(a):

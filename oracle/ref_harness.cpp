@@ -63,6 +63,8 @@ StaticFusion::StaticFusion(unsigned int res_factor)
     depthWarpedRefference = MatrixXf::Zero(rows, cols); intensityWarpedRefference = MatrixXf::Zero(rows, cols);  /* :158-159 */
     T_odometry.setIdentity(); twist_odometry.fill(0.f); twist_level_odometry.fill(0.f); est_cov.fill(0.f);
     for (int i = 0; i < NUM_CLUSTERS; i++) for (int j = 0; j < NUM_CLUSTERS; j++) connectivity[i][j] = (i == j);
+    depth_mm = cv::Mat(height, width, CV_16U, 0.0);                                             /* :161-162 */
+    color_full = cv::Mat(height, width, CV_8UC3, cv::Scalar(0,0,0));
     confidence = 0.25f; depth_max = 4.5f; reconstruction = nullptr; gui = nullptr;               /* :167-168 */
 }
 
@@ -131,6 +133,35 @@ int ref_get_residual_image(void* h, const char* name, float* out) {
     else return -2;
     return 0;
 }
+/* ---- image-sequence loader (FrontEnd.cpp:183-254): the reference's own loadAssoc / loadImageFromSequenceAssoc ---- */
+/* register a decoded image under a file name for the shim's cv::imread: type 16 = 8-bit BGR, 2 = 16-bit single channel */
+void ref_register_image(const char* name, const void* data, int rows, int cols, int type) {
+    cv::Mat m(rows, cols, type, 0.0);
+    std::memcpy(m.data, data, (size_t)rows * cols * cv::Mat::elem(type));
+    cv::shim_image_registry()[name] = m;
+}
+void ref_clear_images(void) { cv::shim_image_registry().clear(); }
+int ref_load_image_from_sequence_assoc(void* h, const char* depthFile, const char* rgbFile, int res_factor) {
+    return static_cast<StaticFusion*>(h)->loadImageFromSequenceAssoc(depthFile, rgbFile, (unsigned)res_factor) ? 1 : 0;
+}
+void ref_get_current(void* h, float* depth, float* intensity, unsigned short* depth_mm, unsigned char* color_full) {
+    StaticFusion& s = *static_cast<StaticFusion*>(h);
+    out_rowmajor(s.depthCurrent, s.rows, s.cols, depth); out_rowmajor(s.intensityCurrent, s.rows, s.cols, intensity);
+    std::memcpy(depth_mm, s.depth_mm.data, sizeof(unsigned short) * s.rows * s.cols);
+    std::memcpy(color_full, s.color_full.data, 3u * s.rows * s.cols);
+}
+/* loadAssoc: returns the number of entries (or -1 when the file cannot be opened); entry k is read back with ref_assoc_entry */
+static std::vector<double> g_assoc_ts; static std::vector<std::string> g_assoc_depth, g_assoc_color;
+int ref_load_assoc(void* h, const char* dir, const char* assocFile) {
+    g_assoc_ts.clear(); g_assoc_depth.clear(); g_assoc_color.clear();
+    if (!static_cast<StaticFusion*>(h)->loadAssoc(dir, assocFile, g_assoc_ts, g_assoc_depth, g_assoc_color)) return -1;
+    return (int)g_assoc_ts.size();
+}
+double ref_assoc_entry(int k, char* depth_path, char* color_path, int cap) {
+    std::snprintf(depth_path, cap, "%s", g_assoc_depth[k].c_str()); std::snprintf(color_path, cap, "%s", g_assoc_color[k].c_str());
+    return g_assoc_ts[k];
+}
+
 void ref_kmeans(void* h) { StaticFusion& s = *static_cast<StaticFusion*>(h); s.kMeans3DCoord(); s.createClustersPyramidUsingKMeans(); }
 /* one warp of pyramid level `image_level` with the current T_odometry (FrontEnd.cpp:775) */
 void ref_warp_level(void* h, int image_level) {

@@ -505,20 +505,71 @@ public:
 }  // namespace mrpt
 
 /* ------------------------------------------------------------------------------------------------
- * OpenCV sliver: StaticFusion.h only declares two cv::Mat members; the solver never touches them
+ * OpenCV sliver.  StaticFusion.h declares two cv::Mat members (depth_mm, color_full); the solver never
+ * touches them, the image-sequence loader (FrontEnd.cpp:216-254) does: imread, at<>, convertTo, Vec3b.
+ * Stand-ins for library internals that are not in the reference tree:
+ *   - imread() returns images the test harness registered under that file name, in the layout OpenCV's
+ *     decoder produces (8-bit 3-channel BGR for CV_LOAD_IMAGE_COLOR, the file's own depth for flag -1):
+ *     PNG decoding itself is libpng's job, not the reference's;
+ *   - convertTo(dst, type, alpha) computes saturate_cast<dst>(float(src) * float(alpha)) per element, the
+ *     arithmetic of OpenCV's cvtScale_ for 16U sources (work type float);
+ *   - Vec3b(float, float, float) converts each argument to uchar implicitly (C++ truncation), as the
+ *     cv::Vec<uchar,3>(uchar, uchar, uchar) constructor the reference's call resolves to does.
  * ---------------------------------------------------------------------------------------------- */
+#include <map>
+#include <memory>
+#ifndef CV_16U
+#define CV_8U 0
+#define CV_16U 2
+#define CV_32F 5
+#define CV_8UC3 16
+#define CV_32FC1 5
+#define CV_LOAD_IMAGE_COLOR 1
+#endif
 namespace cv {
 struct Scalar { Scalar(double = 0, double = 0, double = 0, double = 0) {} };
-struct Mat {
-    Mat() {}
-    Mat(int, int, int, double) {}
-    Mat(int, int, int, const Scalar&) {}
+struct Vec3b {
+    unsigned char val[3];
+    Vec3b() { val[0] = val[1] = val[2] = 0; }
+    Vec3b(unsigned char a, unsigned char b, unsigned char c) { val[0] = a; val[1] = b; val[2] = c; }
+    unsigned char& operator[](int i) { return val[i]; }
+    const unsigned char& operator[](int i) const { return val[i]; }
 };
+struct Mat {
+    int rows = 0, cols = 0, type_ = 0;
+    std::shared_ptr<std::vector<unsigned char> > store;  /* shallow copies, like cv::Mat */
+    unsigned char* data = nullptr;
+    static size_t elem(int type) { return type == CV_8UC3 ? 3 : type == CV_16U ? 2 : type == CV_32F ? 4 : 1; }
+    void create(int r, int c, int type) {
+        rows = r; cols = c; type_ = type;
+        store = std::make_shared<std::vector<unsigned char> >((size_t)r * c * elem(type), (unsigned char)0);
+        data = store->data();
+    }
+    Mat() {}
+    Mat(int r, int c, int type, double) { create(r, c, type); }
+    Mat(int r, int c, int type, const Scalar&) { create(r, c, type); }
+    int type() const { return type_; }
+    template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + ((size_t)r * cols + c) * sizeof(T)); }
+    template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + ((size_t)r * cols + c) * sizeof(T)); }
+    void convertTo(Mat& dst, int rtype, double alpha = 1.0) const {
+        assert(type_ == CV_16U && (rtype == CV_32F || rtype == CV_16U));
+        Mat out; out.create(rows, cols, rtype);
+        const float a = (float)alpha;
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) {
+                const float v = (float)at<unsigned short>(r, c) * a;
+                if (rtype == CV_32F) out.at<float>(r, c) = v;
+                else { const float q = std::nearbyint(v); out.at<unsigned short>(r, c) = (unsigned short)(q < 0.f ? 0.f : q > 65535.f ? 65535.f : q); }
+            }
+        dst = out;
+    }
+};
+inline std::map<std::string, Mat>& shim_image_registry() { static std::map<std::string, Mat> r; return r; }
+inline Mat imread(const std::string& name, int /*flags*/) {
+    auto it = shim_image_registry().find(name);
+    return it == shim_image_registry().end() ? Mat() : it->second;
+}
 }  // namespace cv
-#ifndef CV_16U
-#define CV_16U 2
-#define CV_8UC3 16
-#endif
 
 /* the GL back-end and the GUI are out of scope: StaticFusion.h only holds pointers to them */
 class Reconstruction;

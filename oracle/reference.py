@@ -1,5 +1,5 @@
 """ctypes binding of oracle/_ref/libsf_ref.so: the REFERENCE's own solver sources (KMeans.cpp,
-SegmentationBackground.cpp, FrontEnd.cpp lines 256-1146, StaticFusion.h), compiled unmodified from
+SegmentationBackground.cpp, FrontEnd.cpp lines 183-1146, StaticFusion.h), compiled unmodified from
 /root/reference against the header shim in oracle/ref_shim (oracle/Makefile target `ref`).
 
 TEST INFRASTRUCTURE ONLY.  /root/reference exists only in the build container: `build()` compiles when it
@@ -78,6 +78,14 @@ def lib():
         L.ref_get_kmeans.argtypes = [vp, fp, C.POINTER(C.c_uint8)]
         L.ref_get_pose.argtypes = [vp, fp, fp, fp, fp, fp]
         L.ref_get_seg.argtypes = [vp, fp, fp, fp]
+        L.ref_register_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_load_image_from_sequence_assoc.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_load_image_from_sequence_assoc.restype = C.c_int
+        L.ref_get_current.argtypes = [vp, fp, fp, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)]
+        L.ref_load_assoc.argtypes = [vp, C.c_char_p, C.c_char_p]
+        L.ref_load_assoc.restype = C.c_int
+        L.ref_assoc_entry.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_assoc_entry.restype = C.c_double
         _lib = L
     return _lib
 
@@ -170,6 +178,32 @@ class Reference:
         self.build_segm_image()
         self.buffer_push(index)
         return self.T()
+
+    def load_image_from_sequence_assoc(self, bgr, depth_raw, res_factor):
+        """The reference's own StaticFusion::loadImageFromSequenceAssoc (FrontEnd.cpp:216-254) on decoded images handed to
+        the shim's cv::imread: returns (intensityCurrent, depthCurrent, depth_mm, color_full), row-major."""
+        b = np.ascontiguousarray(bgr, dtype=np.uint8)
+        d = np.ascontiguousarray(depth_raw, dtype=np.uint16)
+        self.L.ref_clear_images()
+        self.L.ref_register_image(b"rgb.png", b.ctypes.data, b.shape[0], b.shape[1], 16)
+        self.L.ref_register_image(b"depth.png", d.ctypes.data, d.shape[0], d.shape[1], 2)
+        end = self.L.ref_load_image_from_sequence_assoc(self.h, b"depth.png", b"rgb.png", int(res_factor))
+        assert end == 0
+        dep = np.zeros((self.rows, self.cols), np.float32); inten = np.zeros((self.rows, self.cols), np.float32)
+        mm = np.zeros((self.rows, self.cols), np.uint16); col = np.zeros((self.rows, self.cols, 3), np.uint8)
+        self.L.ref_get_current(self.h, _fp(dep), _fp(inten), mm.ctypes.data_as(C.POINTER(C.c_uint16)), col.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return inten, dep, mm, col
+
+    def load_assoc(self, directory, assoc_file):
+        """The reference's own StaticFusion::loadAssoc (FrontEnd.cpp:183-214): (timestamps, filesDepth, filesColor) or None."""
+        n = self.L.ref_load_assoc(self.h, directory.encode(), assoc_file.encode())
+        if n < 0:
+            return None
+        ts, fd, fc = [], [], []
+        a, b = C.create_string_buffer(4096), C.create_string_buffer(4096)
+        for k in range(n):
+            ts.append(self.L.ref_assoc_entry(k, a, b, 4096)); fd.append(a.value.decode()); fc.append(b.value.decode())
+        return ts, fd, fc
 
     def warp_level(self, image_level):
         self.L.ref_warp_level(self.h, image_level)

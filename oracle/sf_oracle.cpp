@@ -1742,6 +1742,62 @@ void orc_filter_depth(const uint16_t* depth_mm, int rows, int cols, float max_de
     filter_depth(depth_mm, rows, cols, max_depth_m, exact, out);
 }
 float orc_det_expf(float a) { return det_expf(a); }
+
+/* StaticFusion::loadImageFromSequenceAssoc, FrontEnd.cpp:216-254 (conversion half) */
+void orc_convert_frame(const uint8_t* bgr, const uint16_t* depth_raw, int full_rows, int full_cols, int res_factor,
+                       float* intensity, float* depth, uint16_t* depth_mm, uint8_t* color) {
+    const int height = full_rows / res_factor, width = full_cols / res_factor;
+    const float norm_factor = 1.f / 255.f;                                               /* :218 */
+    const float mm_to_m = (float)(1.0 / 1000.0);                                         /* :243 convertTo(CV_32FC1, 1.0/1000.0): float(src) * float(alpha) */
+    for (int v = 0; v < height; v++)
+        for (int u = 0; u < width; u++) {
+            const size_t src = (size_t)(height * res_factor - res_factor * v - 1) * full_cols + (size_t)res_factor * u;  /* :231 vertical flip + decimation */
+            const size_t dst = (size_t)v * width + u;
+            const float r = norm_factor * (float)bgr[3 * src + 0];                       /* :232-234: channel 0 of a BGR image is named r */
+            const float g = norm_factor * (float)bgr[3 * src + 1];
+            const float b = norm_factor * (float)bgr[3 * src + 2];
+            if (intensity) intensity[dst] = 0.299f * r + 0.587f * g + 0.114f * b;        /* :236, left to right */
+            if (color) {                                                                 /* :237 Vec3b(r*255, g*255, b*255): float -> uchar truncation */
+                color[3 * dst + 0] = (uint8_t)(r * 255); color[3 * dst + 1] = (uint8_t)(g * 255); color[3 * dst + 2] = (uint8_t)(b * 255);
+            }
+            if (depth) depth[dst] = (float)depth_raw[src] * mm_to_m;                     /* :249 */
+            if (depth_mm) depth_mm[dst] = depth_raw[src];                                /* :244,250 convertTo(CV_16U, 1.0) is a copy */
+        }
+}
+
+/* Reconstruction.cpp:256,265: currPose = currPose * (*inPose), Eigen Matrix4f product (sequential k = 0..3 float sums) */
+void orc_pose_compose(const float A[16], const float B[16], float out[16]) {
+    float r[16];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            float s = A[i * 4 + 0] * B[0 * 4 + j];
+            for (int k = 1; k < 4; k++) s += A[i * 4 + k] * B[k * 4 + j];
+            r[i * 4 + j] = s;
+        }
+    std::memcpy(out, r, sizeof(r));
+}
+
+/* Eigen::Quaternionf(const Matrix3f&) as used by Datasets.cpp:259 and Reconstruction.cpp:480 (Eigen 3 Quaternion.h,
+ * quaternionbase_assign_impl<Other,3,3>): not in the reference tree, published algorithm restated */
+void orc_quat_from_rotation(const float T[16], float q[4]) {
+    auto m = [&](int r, int c) { return T[r * 4 + c]; };
+    float t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > 0.f) {
+        t = std::sqrt(t + 1.f);
+        q[3] = 0.5f * t;
+        t = 0.5f / t;
+        q[0] = (m(2, 1) - m(1, 2)) * t; q[1] = (m(0, 2) - m(2, 0)) * t; q[2] = (m(1, 0) - m(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (m(1, 1) > m(0, 0)) i = 1;
+        if (m(2, 2) > m(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.f);
+        q[i] = 0.5f * t;
+        t = 0.5f / t;
+        q[3] = (m(k, j) - m(j, k)) * t; q[j] = (m(j, i) + m(i, j)) * t; q[k] = (m(k, i) + m(i, k)) * t;
+    }
+}
 int orc_get_status(const orc_ctx* c) { return c->status; }
 int orc_get_total_irls(const orc_ctx* c) { return c->total_irls; }
 

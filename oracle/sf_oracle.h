@@ -91,6 +91,21 @@ int  orc_get_residual_image(const orc_ctx* c, const char* name, float* out_rowma
 void orc_filter_depth(const uint16_t* depth_mm, int rows, int cols, float max_depth_m, int exact, float* out);
 float orc_det_expf(float a);
 
+/* Image-sequence loader, conversion half (StaticFusion::loadImageFromSequenceAssoc, FrontEnd.cpp:216-254; the PNG decode
+ * itself is OpenCV/libpng).  bgr: full_rows x full_cols x 3 bytes as cv::imread(..., CV_LOAD_IMAGE_COLOR) returns them;
+ * depth_raw: full_rows x full_cols uint16 (millimetres).  Outputs are (full_rows/res_factor) x (full_cols/res_factor),
+ * row-major, vertically flipped and decimated exactly as the reference does: intensity [0,1], depth metres,
+ * depth_mm (StaticFusion::depth_mm) and colour (StaticFusion::color_full, 3 bytes per pixel).  Pinned bit-for-bit
+ * against the reference's own function (oracle/_ref, tests/test_tum_io.py). */
+void orc_convert_frame(const uint8_t* bgr, const uint16_t* depth_raw, int full_rows, int full_cols, int res_factor,
+                       float* intensity, float* depth, uint16_t* depth_mm, uint8_t* color);
+/* Trajectory bookkeeping of the callers: currPose = currPose * T_odometry in float (Reconstruction.cpp:256,265), the
+ * TUM-format quaternion (Eigen::Quaternionf(Matrix3f), Eigen/src/Geometry/Quaternion.h: trace / largest-diagonal branches)
+ * of Datasets::writeTrajectoryFile (Datasets.cpp:252-266) and Reconstruction::savePly (Reconstruction.cpp:460-484).
+ * Matrices row-major; q = (x, y, z, w). */
+void orc_pose_compose(const float A_rowmajor[16], const float B_rowmajor[16], float out_rowmajor[16]);
+void orc_quat_from_rotation(const float T_rowmajor[16], float q_xyzw[4]);
+
 /* stand-alone stages for unit tests */
 void orc_kmeans(orc_ctx* c); /* kMeans3DCoord + createClustersPyramidUsingKMeans on the current pyramid */
 void orc_warp_level(orc_ctx* c, int image_level, const float T_odometry_rowmajor[16]);
