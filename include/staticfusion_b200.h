@@ -120,6 +120,17 @@ int sf_build_segm_image(sf_ctx* ctx);
 int sf_filter_depth(sf_ctx* ctx, int n_images, const uint16_t* depth_mm, int in_space, float max_depth_m, float* depth_out,
                     int out_space, int col_major_out);
 
+/* ---- image-sequence loader: where depthCurrent / intensityCurrent come from on recorded sequences ---- */
+/* StaticFusion::loadImageFromSequenceAssoc(depthFile, rgbFile, res_factor) (StaticFusion.h:122, FrontEnd.cpp:216-254),
+ * the part after cv::imread: n_images decoded images at full resolution (rows*res_factor x cols*res_factor, row-major;
+ * bgr = 3 bytes per pixel in cv::imread's BGR order, depth_raw = uint16 millimetres) -> rows x cols outputs, vertically
+ * flipped and decimated as the reference does (:231,249): intensity in [0,1] (intensityCurrent), depth in metres
+ * (depthCurrent), depth_mm (StaticFusion::depth_mm) and the 3-byte colour image (StaticFusion::color_full).  Every output
+ * and either input may be NULL.  Buffers are host or device memory (SF_MEM_*); col_major_out = 1 writes the two float
+ * images in the Eigen layout (host only).  PNG decoding stays on the host (the reference uses OpenCV for it). */
+int sf_convert_frames(sf_ctx* ctx, int n_images, const uint8_t* bgr, const uint16_t* depth_raw, int res_factor, int in_space,
+                      float* intensity, float* depth, uint16_t* depth_mm, uint8_t* color_full, int out_space, int col_major_out);
+
 /* ---- 5-frame history: completes the segmentation image exactly as the drivers produce it ---------- */
 /* Stand in for the drivers' writes to depthBuffer / intensityBuffer / odomBuffer[slot % 5] (StaticFusion.h:94-96):
  * sf_buffer_set with explicit images (bootstrap, StaticFusion-datasets.cpp:114-116; T = NULL means identity, else
@@ -188,6 +199,10 @@ int sf_upload_pairs(sf_ctx* ctx, int n_pairs, const float* depth_cur, const floa
 int sf_upload_sequence(sf_ctx* ctx, int n_frames, const float* depth, const float* inten, int in_space,
                        const float* twist_old_in);
 /* Enqueue the whole solve for the uploaded batch on the context's stream; no host synchronisation. */
+/* sf_upload_sequence for frames still in their decoded file form (see sf_convert_frames): the conversion runs on the
+ * device straight into the solver's frame slots, 5 * res_factor^2 bytes per pixel cross PCIe instead of 8. */
+int sf_upload_sequence_raw(sf_ctx* ctx, int n_frames, const uint8_t* bgr, const uint16_t* depth_raw, int res_factor, int in_space,
+                           const float* twist_old_in);
 int sf_launch(sf_ctx* ctx);
 /* Wait for the stream. */
 int sf_sync(sf_ctx* ctx);

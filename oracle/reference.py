@@ -82,10 +82,6 @@ def lib():
         L.ref_load_image_from_sequence_assoc.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
         L.ref_load_image_from_sequence_assoc.restype = C.c_int
         L.ref_get_current.argtypes = [vp, fp, fp, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)]
-        L.ref_load_assoc.argtypes = [vp, C.c_char_p, C.c_char_p]
-        L.ref_load_assoc.restype = C.c_int
-        L.ref_assoc_entry.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int]
-        L.ref_assoc_entry.restype = C.c_double
         _lib = L
     return _lib
 
@@ -194,15 +190,20 @@ class Reference:
         self.L.ref_get_current(self.h, _fp(dep), _fp(inten), mm.ctypes.data_as(C.POINTER(C.c_uint16)), col.ctypes.data_as(C.POINTER(C.c_uint8)))
         return inten, dep, mm, col
 
-    def load_assoc(self, directory, assoc_file):
-        """The reference's own StaticFusion::loadAssoc (FrontEnd.cpp:183-214): (timestamps, filesDepth, filesColor) or None."""
-        n = self.L.ref_load_assoc(self.h, directory.encode(), assoc_file.encode())
+    @staticmethod
+    def load_assoc(directory, assoc_file):
+        """The reference's own StaticFusion::loadAssoc (FrontEnd.cpp:183-214), run by oracle/_ref/ref_assoc in its own
+        process: (timestamps, filesDepth, filesColor) or None when the reference returns false."""
+        lib()
+        txt = subprocess.run([os.path.join(_HERE, "_ref", "ref_assoc"), directory, assoc_file], capture_output=True, text=True, check=True).stdout
+        lines = txt.split("\n")
+        n = int(lines[0])
         if n < 0:
             return None
         ts, fd, fc = [], [], []
-        a, b = C.create_string_buffer(4096), C.create_string_buffer(4096)
         for k in range(n):
-            ts.append(self.L.ref_assoc_entry(k, a, b, 4096)); fd.append(a.value.decode()); fc.append(b.value.decode())
+            t, a, b = lines[1 + k].split("\t")
+            ts.append(float(t)); fd.append(a); fc.append(b)
         return ts, fd, fc
 
     def warp_level(self, image_level):

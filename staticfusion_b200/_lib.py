@@ -32,6 +32,7 @@ EXPORTS = [
     "sf_profile_enable", "sf_profile_read", "sf_profile_read_records", "sf_get_step_stats",
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
     "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
+    "sf_convert_frames", "sf_upload_sequence_raw",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -109,6 +110,8 @@ def lib():
     L.sf_get_per_cluster_average_residual.argtypes = [vp, fp]
     L.sf_set_history.argtypes = [vp, C.c_int]
     L.sf_filter_depth.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, vp, C.c_int, C.c_int]
+    L.sf_convert_frames.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int]
+    L.sf_upload_sequence_raw.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, fp]
     L.sf_stream.argtypes = [vp]
     L.sf_stream.restype = C.c_uint64
     L.sf_last_launch_count.argtypes = [vp]

@@ -64,6 +64,9 @@ struct sf_ctx {
     uint16_t* d_raw = nullptr;
     float* d_filt = nullptr;
     size_t filt_cap = 0;
+    // image-sequence loader scratch (grown on demand): raw inputs and converted outputs of sf_convert_frames
+    uint8_t* d_cvt = nullptr;
+    size_t cvt_cap = 0;
 };
 
 static void drop_graphs(sf_ctx* c) {
@@ -286,7 +289,7 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in); cudaFree(c->d_seed_map);
     cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.active_list); cudaFree(a.work_ctr);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
-    cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt);
+    cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt); cudaFree(c->d_cvt);
     drop_graphs(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -677,6 +680,104 @@ int sf_filter_depth(sf_ctx* c, int n_images, const uint16_t* depth_mm, int in_sp
         }
     }
     CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// image-sequence loader (FrontEnd.cpp:216-254)
+// ---------------------------------------------------------------------------------------------
+static int cvt_reserve(sf_ctx* c, size_t bytes) {
+    if (c->cvt_cap >= bytes) return SF_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_cvt); c->d_cvt = nullptr; c->cvt_cap = 0;
+    CU(cudaMalloc((void**)&c->d_cvt, bytes));
+    c->cvt_cap = bytes;
+    return SF_OK;
+}
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int sf_convert_frames(sf_ctx* c, int n_images, const uint8_t* bgr, const uint16_t* depth_raw, int res_factor, int in_space, float* intensity,
+                      float* depth, uint16_t* depth_mm, uint8_t* color_full, int out_space, int col_major_out) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (n_images < 1 || res_factor < 1) return fail(SF_E_INVALID, "n_images and res_factor must be >= 1");
+    if (!bgr && !depth_raw) return fail(SF_E_INVALID, "no input image");
+    if ((!bgr && (intensity || color_full)) || (!depth_raw && (depth || depth_mm))) return fail(SF_E_INVALID, "output requested without its input");
+    if (col_major_out && out_space == SF_MEM_DEVICE) return fail(SF_E_INVALID, "column-major output is a host-side conversion");
+    CU(cudaSetDevice(c->device));
+    const size_t P = c->a.P0, n = (size_t)n_images, Pf = P * res_factor * res_factor;
+    const bool need_in = in_space != SF_MEM_DEVICE, need_out = out_space != SF_MEM_DEVICE;
+    // scratch layout: [bgr in][depth in][intensity][depth][depth_mm][colour]
+    const size_t o_bgr = 0, o_raw = o_bgr + align256(need_in && bgr ? 3 * Pf * n : 0), o_i = o_raw + align256(need_in && depth_raw ? 2 * Pf * n : 0);
+    const size_t o_d = o_i + align256(need_out && intensity ? 4 * P * n : 0), o_mm = o_d + align256(need_out && depth ? 4 * P * n : 0);
+    const size_t o_col = o_mm + align256(need_out && depth_mm ? 2 * P * n : 0), total = o_col + align256(need_out && color_full ? 3 * P * n : 0);
+    if (total) { const int rc = cvt_reserve(c, total); if (rc) return rc; }
+    const uint8_t* s_bgr = bgr;
+    const uint16_t* s_raw = depth_raw;
+    if (need_in && bgr) { CU(cudaMemcpyAsync(c->d_cvt + o_bgr, bgr, 3 * Pf * n, cudaMemcpyHostToDevice, c->stream)); s_bgr = c->d_cvt + o_bgr; }
+    if (need_in && depth_raw) { CU(cudaMemcpyAsync(c->d_cvt + o_raw, depth_raw, 2 * Pf * n, cudaMemcpyHostToDevice, c->stream)); s_raw = (const uint16_t*)(c->d_cvt + o_raw); }
+    float* t_i = intensity ? (need_out ? (float*)(c->d_cvt + o_i) : intensity) : nullptr;
+    float* t_d = depth ? (need_out ? (float*)(c->d_cvt + o_d) : depth) : nullptr;
+    uint16_t* t_mm = depth_mm ? (need_out ? (uint16_t*)(c->d_cvt + o_mm) : depth_mm) : nullptr;
+    uint8_t* t_col = color_full ? (need_out ? c->d_cvt + o_col : color_full) : nullptr;
+    launch_convert_frames(s_bgr, s_raw, c->p.rows, c->p.cols, res_factor, n_images, t_i, t_d, P, t_mm, t_col, c->stream);
+    CU(cudaGetLastError());
+    if (need_out) {
+        std::vector<float> tmp;
+        const int rows = c->p.rows, cols = c->p.cols;
+        auto fetch_f32 = [&](float* dst, const float* dev) -> int {
+            if (!col_major_out) { CU(cudaMemcpyAsync(dst, dev, 4 * P * n, cudaMemcpyDeviceToHost, c->stream)); return SF_OK; }
+            tmp.resize(P * n);
+            CU(cudaMemcpyAsync(tmp.data(), dev, 4 * P * n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (size_t k = 0; k < n; k++)
+                for (int v = 0; v < rows; v++)
+                    for (int u = 0; u < cols; u++) dst[k * P + (size_t)u * rows + v] = tmp[k * P + (size_t)v * cols + u];
+            return SF_OK;
+        };
+        int rc;
+        if (intensity && (rc = fetch_f32(intensity, t_i))) return rc;
+        if (depth && (rc = fetch_f32(depth, t_d))) return rc;
+        if (depth_mm) CU(cudaMemcpyAsync(depth_mm, t_mm, 2 * P * n, cudaMemcpyDeviceToHost, c->stream));
+        if (color_full) CU(cudaMemcpyAsync(color_full, t_col, 3 * P * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return SF_OK;
+}
+
+int sf_upload_sequence_raw(sf_ctx* c, int n_frames, const uint8_t* bgr, const uint16_t* depth_raw, int res_factor, int in_space,
+                           const float* twist_old_in) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (n_frames < 2 || n_frames - 1 > c->max_batch) return fail(SF_E_INVALID, "n_frames-1 must be in [1, max_batch]");
+    if (!bgr || !depth_raw) return fail(SF_E_INVALID, "NULL image pointer");
+    if (res_factor < 1) return fail(SF_E_INVALID, "res_factor must be >= 1");
+    CU(cudaSetDevice(c->device));
+    const size_t P = c->a.P0, n = (size_t)n_frames, Pf = P * res_factor * res_factor;
+    const uint8_t* s_bgr = bgr;
+    const uint16_t* s_raw = depth_raw;
+    if (in_space != SF_MEM_DEVICE) {
+        const size_t o_raw = align256(3 * Pf * n);
+        const int rc = cvt_reserve(c, o_raw + align256(2 * Pf * n));
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->d_cvt, bgr, 3 * Pf * n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_cvt + o_raw, depth_raw, 2 * Pf * n, cudaMemcpyHostToDevice, c->stream));
+        s_bgr = c->d_cvt; s_raw = (const uint16_t*)(c->d_cvt + o_raw);
+    }
+    // frame k converts straight into the level-0 slot of its pyramids (prediction := previous raw frame)
+    launch_convert_frames(s_bgr, s_raw, c->p.rows, c->p.cols, res_factor, n_frames, c->a.pyr_i, c->a.pyr_d, c->a.pyr_stride, nullptr, nullptr, c->stream);
+    CU(cudaGetLastError());
+    const int n_pairs = n_frames - 1;
+    std::vector<int>&ci = c->h_ci, &pi = c->h_pi;
+    if ((int)ci.size() != n_pairs || ci[0] != 1 || pi[0] != 0) {
+        CU(cudaStreamSynchronize(c->stream));
+        ci.resize(n_pairs); pi.resize(n_pairs);
+        for (int k = 0; k < n_pairs; k++) { ci[k] = k + 1; pi[k] = k; }
+    }
+    CU(cudaMemcpyAsync(c->d_cur_idx, ci.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pred_idx, pi.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    int rc;
+    if ((rc = upload_twist(c, n_pairs, twist_old_in))) return rc;
+    if (twist_old_in) CU(cudaStreamSynchronize(c->stream));
+    c->n_pairs = n_pairs; c->n_frames = n_frames; c->uploaded = true; c->solved = false; c->is_sequence = true;
     return SF_OK;
 }
 

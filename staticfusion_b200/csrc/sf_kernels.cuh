@@ -80,6 +80,10 @@ int launch_history(const Arena& a, const DevParams& p, const LevelGeom& g0, int 
 // Reconstruction::getFilteredDepth: n images of rows x cols u16 millimetres -> float metres (strides in elements)
 int launch_filter_depth(const uint16_t* in, float* out, int rows, int cols, int n, size_t in_stride, size_t out_stride, float max_depth_m,
                         cudaStream_t stream);
+// StaticFusion::loadImageFromSequenceAssoc, conversion half: n decoded full-resolution images -> rows x cols outputs
+// (f32_stride = elements between consecutive intensity / depth images, so they can land in the pyramids' level-0 slots)
+int launch_convert_frames(const uint8_t* bgr, const uint16_t* depth_raw, int rows, int cols, int res_factor, int n, float* intensity, float* depth,
+                          size_t f32_stride, uint16_t* depth_mm, uint8_t* color, cudaStream_t stream);
 int launch_segm_image(const Arena& a, const LevelGeom& g0, const LaunchCfg& c);  // buildSegmImage
 
 }  // namespace sf

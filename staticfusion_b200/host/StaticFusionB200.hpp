@@ -9,12 +9,14 @@
 // pass `m.data()` straight through.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <limits>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/staticfusion_b200.h"
+#include "TumIO.hpp"
 
 namespace sfb200 {
 
@@ -74,6 +76,9 @@ public:
     std::vector<Matrix4f> odomBuffer;
     int bufferLength = 5;
     float perClusterAverageResidual[SF_NUM_CLUSTERS];  // NaN until computeResidualsAgainstPreviousImage ran (FrontEnd.cpp:105)
+    // ---- what the image-sequence loader fills besides depthCurrent / intensityCurrent (StaticFusion.h:71; cv::Mat there) ----
+    std::vector<uint16_t> depth_mm;   // rows x cols, row-major millimetres  (handed to fuseFrame / getFilteredDepth)
+    std::vector<uint8_t> color_full;  // rows x cols x 3, row-major            (handed to fuseFrame)
     int irls_iterations = 0, status = 0;  // extras: SF_STATUS_* bits replace the reference's undefined behaviour
 
     // StaticFusion::StaticFusion(res_factor), FrontEnd.cpp:52-181 (solver part only)
@@ -101,6 +106,30 @@ public:
     StaticFusion(const StaticFusion&) = delete;
     StaticFusion& operator=(const StaticFusion&) = delete;
 
+    // StaticFusion::loadAssoc, FrontEnd.cpp:183
+    bool loadAssoc(const std::string& dir, const std::string& assocFile, std::vector<double>& timestamps,
+                   std::vector<std::string>& filesDepth, std::vector<std::string>& filesColor) const {
+        return sfb200::loadAssoc(dir, assocFile, timestamps, filesDepth, filesColor);
+    }
+    // StaticFusion::loadImageFromSequenceAssoc, FrontEnd.cpp:216: returns true at the end of the sequence (colour image
+    // missing).  PNG decode on the host, flip / decimation / conversions on the device (sf_convert_frames).
+    bool loadImageFromSequenceAssoc(const std::string& depthFile, const std::string& rgbFile, unsigned int res_factor) {
+        std::vector<uint8_t> bgr;
+        std::vector<uint16_t> raw;
+        int r = 0, c = 0, rd = 0, cd = 0;
+        if (!imread_color_bgr(rgbFile, bgr, r, c)) {
+            std::printf("End of sequence (or color image not found...)\n");
+            return true;
+        }
+        if (!imread_depth_u16(depthFile, raw, rd, cd)) throw std::runtime_error("staticfusion_b200: depth image not found: " + depthFile);
+        if (r != (int)(height * res_factor) || c != (int)(width * res_factor) || rd != r || cd != c)
+            throw std::runtime_error("staticfusion_b200: images must be (height x width) * res_factor");
+        ensure();
+        depth_mm.resize((size_t)rows * cols); color_full.resize((size_t)rows * cols * 3);
+        check(sf_convert_frames(ctx_, 1, bgr.data(), raw.data(), (int)res_factor, SF_MEM_HOST, intensityCurrent.data(), depthCurrent.data(),
+                                depth_mm.data(), color_full.data(), SF_MEM_HOST, 1));
+        return false;
+    }
     // StaticFusion::createImagePyramid(bool old_im), FrontEnd.cpp:256
     void createImagePyramid(bool old_im) {
         ensure();

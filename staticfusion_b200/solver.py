@@ -154,6 +154,38 @@ class StaticFusionSolver:
         check(self.L.sf_filter_depth(self.h, n, src.data_ptr(), MEM_DEVICE, float(max_depth), out.data_ptr(), MEM_DEVICE, 0))
         return out
 
+    def convertFrames(self, bgr, depth_raw, res_factor: int = 2):
+        """StaticFusion::loadImageFromSequenceAssoc (FrontEnd.cpp:216-254) after cv::imread: decoded BGR uint8
+        (H, W, 3) / (n, H, W, 3) and uint16 millimetre depth (H, W) / (n, H, W) with H = rows * res_factor ->
+        (intensity f32, depth f32 metres, depth_mm u16, color_full u8 x 3), flipped and decimated on the device."""
+        b = np.ascontiguousarray(bgr, np.uint8)
+        d = np.ascontiguousarray(depth_raw, np.uint16)
+        single = d.ndim == 2
+        n = 1 if single else d.shape[0]
+        if d.shape[-2:] != (self.rows * res_factor, self.cols * res_factor) or b.shape[:-1] != d.shape or b.shape[-1] != 3:
+            raise ValueError("images must be (rows * res_factor, cols * res_factor) with 3-channel colour")
+        lead = () if single else (n,)
+        inten = np.zeros(lead + (self.rows, self.cols), np.float32)
+        dep = np.zeros(lead + (self.rows, self.cols), np.float32)
+        mm = np.zeros(lead + (self.rows, self.cols), np.uint16)
+        col = np.zeros(lead + (self.rows, self.cols, 3), np.uint8)
+        check(self.L.sf_convert_frames(self.h, n, b.ctypes.data, d.ctypes.data, int(res_factor), MEM_HOST, inten.ctypes.data, dep.ctypes.data,
+                                       mm.ctypes.data, col.ctypes.data, MEM_HOST, 0))
+        return inten, dep, mm, col
+
+    def upload_sequence_raw(self, bgr, depth_raw, res_factor: int = 2, twist_old=None):
+        """upload_sequence for decoded file images (see convertFrames); numpy (host) or CUDA uint8 / uint16 tensors."""
+        nf = int(depth_raw.shape[0])
+        if isinstance(bgr, np.ndarray):
+            b, d = np.ascontiguousarray(bgr, np.uint8), np.ascontiguousarray(depth_raw, np.uint16)
+            pb, pd, space = b.ctypes.data, d.ctypes.data, MEM_HOST
+        else:
+            b, d = bgr.contiguous(), depth_raw.contiguous()
+            pb, pd, space = b.data_ptr(), d.data_ptr(), (MEM_DEVICE if b.is_cuda else MEM_HOST)
+        tw = None if twist_old is None else np.ascontiguousarray(twist_old, np.float32)
+        check(self.L.sf_upload_sequence_raw(self.h, nf, pb, pd, int(res_factor), space, None if tw is None else _fp(tw)))
+        self._n = nf - 1
+
     # 5-frame history of the drivers (StaticFusion.h:92-96, StaticFusion-datasets.cpp:114-116, 175-184)
     def bufferSet(self, slot: int, depth, intensity, T=None):
         """depthBuffer[slot % 5] = depth; intensityBuffer[..] = intensity; odomBuffer[..] = T (4x4 math matrix, None = identity)."""
