@@ -218,6 +218,9 @@ int sf_download_range(sf_ctx* ctx, int first_pair, int n, float* T_odometry, flo
 uint64_t sf_stream(sf_ctx* ctx);
 /* Number of kernel launches enqueued by the last sf_launch. */
 int sf_last_launch_count(sf_ctx* ctx);
+/* Number of concurrent pair ranges (streams) the schedule of the current batch is cut into: 1 for small batches, up to 3
+ * for large ones (environment variable SF_LANES overrides).  The result does not depend on it. */
+int sf_last_lane_count(sf_ctx* ctx);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
 #define SF_PROF_CLASSES 9 /* 0 init, 1 pyramid, 2 clustering, 3 warp, 4 linearise, 5 irls_pass1, 6 irls_pass2, 7 pose_update, 8 finish */

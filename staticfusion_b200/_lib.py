@@ -32,7 +32,7 @@ EXPORTS = [
     "sf_profile_enable", "sf_profile_read", "sf_profile_read_records", "sf_get_step_stats",
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
     "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
-    "sf_convert_frames", "sf_upload_sequence_raw",
+    "sf_convert_frames", "sf_upload_sequence_raw", "sf_last_lane_count",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -115,6 +115,7 @@ def lib():
     L.sf_stream.argtypes = [vp]
     L.sf_stream.restype = C.c_uint64
     L.sf_last_launch_count.argtypes = [vp]
+    L.sf_last_lane_count.argtypes = [vp]
     L.sf_debug_set_stop_step.argtypes = [vp, C.c_int]
     L.sf_debug_get_plane.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, fp]
     L.sf_debug_get_labels.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]

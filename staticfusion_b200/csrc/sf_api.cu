@@ -3,6 +3,7 @@
 // The host enqueues a static schedule (runSolver's loop nest, FrontEnd.cpp:1094-1132, unrolled to its
 // maximum trip counts); all data-dependent exits are per-pair device flags, so one batch is solved
 // without any host synchronisation.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -56,7 +57,7 @@ struct sf_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     // the static schedule captured once per (batch shape, stop step) and replayed: removes ~500 launch gaps per solve
-    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history; cudaGraphExec_t exec; int launches; };
+    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history, lanes; cudaGraphExec_t exec; int launches; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
     int fused_max_tiles = 300;  // levels with at most this many 64-pixel tiles per pair run the fused IRLS kernel (SF_FUSED_MAX_TILES)
@@ -64,6 +65,17 @@ struct sf_ctx {
     uint16_t* d_raw = nullptr;
     float* d_filt = nullptr;
     size_t filt_cap = 0;
+    // lanes: a large batch is cut into contiguous pair ranges that run the per-pair schedule on their own streams (forked
+    // and joined inside the captured graph), so one range's latency-bound kernels (k-means, solves, pose update, IRLS tail
+    // launches) overlap the other ranges' streaming kernels.  Pairs are independent and every sum is an integer sum, so the
+    // result does not depend on the cut.  Lane 0 is the context's stream.  SF_LANES overrides the automatic choice.
+    static constexpr int MAX_LANES = 4;
+    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    int* d_lane_gcount = nullptr;    // [MAX_LANES][4]
+    int* d_iter_list = nullptr;      // [2][max_batch]
+    int* d_lane_work_ctr = nullptr;  // [MAX_LANES][MAX_WORK_CTRS]
+    int lanes_override = 0, last_lanes = 1;
     // image-sequence loader scratch (grown on demand): raw inputs and converted outputs of sf_convert_frames
     uint8_t* d_cvt = nullptr;
     size_t cvt_cap = 0;
@@ -226,9 +238,10 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.warp_d, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.warp_i, sizeof(float) * a.P0 * F);
     ok = ok && alloc((void**)&a.tiles, tiles_per_pair(a.P0) * TILE_BYTES * F);
-    ok = ok && alloc((void**)&a.gcount, sizeof(int) * 2);
     ok = ok && alloc((void**)&a.active_list, sizeof(int) * F);
-    ok = ok && alloc((void**)&a.work_ctr, sizeof(int) * MAX_WORK_CTRS);
+    ok = ok && alloc((void**)&c->d_iter_list, sizeof(int) * 2 * F);
+    ok = ok && alloc((void**)&c->d_lane_gcount, sizeof(int) * 4 * sf_ctx::MAX_LANES);
+    ok = ok && alloc((void**)&c->d_lane_work_ctr, sizeof(int) * MAX_WORK_CTRS * sf_ctx::MAX_LANES);
     if (ok && (flags & 1)) ok = alloc((void**)&a.dbg, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
     ok = ok && alloc((void**)&a.out, sizeof(PairOut) * F);
@@ -245,6 +258,15 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
         return fail(SF_E_NOMEM, msg);
     }
     a.cur_idx = c->d_cur_idx; a.pred_idx = c->d_pred_idx;
+    a.gcount = c->d_lane_gcount; a.work_ctr = c->d_lane_work_ctr;  // lane 0's slices
+    a.iter_list0 = c->d_iter_list; a.iter_list1 = c->d_iter_list + F;
+    if (const char* e = std::getenv("SF_LANES")) c->lanes_override = std::atoi(e);
+    c->lane_stream[0] = c->stream;
+    for (int l = 1; l < sf_ctx::MAX_LANES; l++) {
+        if (cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming) != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, "lane stream creation failed"); }
+    }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, "event creation failed"); }
     if (c->levels > 1) {  // seed labelling of level 1, KMeans.cpp:87-101 (integer arithmetic; 24 = no seed within range)
         const LevelGeom& g1 = c->geom[1];
         std::vector<uint8_t> seed((size_t)g1.P);
@@ -267,7 +289,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     cudaMemsetAsync(a.acc_d, 0, sizeof(long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.tiles, 0xff, tiles_per_pair(a.P0) * TILE_BYTES * F, c->stream);  // every label byte = invalid
-    cudaMemsetAsync(a.gcount, 0, sizeof(int) * 2, c->stream);
+    cudaMemsetAsync(c->d_lane_gcount, 0, sizeof(int) * 4 * sf_ctx::MAX_LANES, c->stream);
     cudaMemsetAsync(a.pcar, 0xff, sizeof(float) * NC * F, c->stream);  // all-ones = quiet NaN (FrontEnd.cpp:105)
     cudaMemsetAsync(a.ring_d, 0, sizeof(float) * a.P0 * 5, c->stream);
     cudaMemsetAsync(a.ring_i, 0, sizeof(float) * a.P0 * 5, c->stream);
@@ -287,10 +309,13 @@ void sf_destroy(sf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     Arena& a = c->a;
     cudaFree(a.pyr_d); cudaFree(a.pyr_i); cudaFree(c->d_cur_idx); cudaFree(c->d_pred_idx); cudaFree(c->d_twist_in); cudaFree(c->d_seed_map);
-    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.gcount); cudaFree(a.active_list); cudaFree(a.work_ctr);
+    cudaFree(a.labels); cudaFree(a.acc_d); cudaFree(a.acc_iw); cudaFree(a.warp_d); cudaFree(a.warp_i); cudaFree(a.tiles); cudaFree(a.dbg); cudaFree(a.active_list);
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
     cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt); cudaFree(c->d_cvt);
     drop_graphs(c);
+    cudaFree(c->d_lane_gcount); cudaFree(c->d_lane_work_ctr); cudaFree(c->d_iter_list);
+    for (int l = 1; l < sf_ctx::MAX_LANES; l++) { if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -379,16 +404,41 @@ int sf_upload_sequence(sf_ctx* c, int n_frames, const float* depth, const float*
 // ---------------------------------------------------------------------------------------------
 // schedule
 // ---------------------------------------------------------------------------------------------
-static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
+// the arena as one lane sees it: every per-pair array starts at the lane's first pair, control cells are the lane's own
+static Arena lane_arena(const sf_ctx* c, int lane, int lo) {
+    Arena a = c->a;
+    const size_t o = (size_t)lo;
+    a.cur_idx += o; a.pred_idx += o;
+    a.labels += o * a.pyr_stride;
+    a.acc_d += o * a.P0; a.acc_iw += o * a.P0; a.warp_d += o * a.P0; a.warp_i += o * a.P0;
+    a.tiles += o * tiles_per_pair(a.P0) * TILE_BYTES;
+    if (a.dbg) a.dbg += o * NPLANES * a.P0;
+    a.active_list += o; a.iter_list0 += o; a.iter_list1 += o;
+    a.gcount = c->d_lane_gcount + 4 * lane;
+    a.work_ctr = c->d_lane_work_ctr + (size_t)MAX_WORK_CTRS * lane;
+    a.ctl += o; a.out += o;
+    a.b_perpixel += o * a.P0;
+    a.pcar += o * NC;
+    if (a.trace) a.trace += o * SF_TRACE_STEP * a.trace_steps;
+    a.stepstat += o * 2 * a.trace_steps;
+    return a;
+}
+
+static int choose_lanes(const sf_ctx* c) {
+    if (c->prof_on) return 1;  // per-kernel events time each kernel alone on one stream
+    int n = c->lanes_override > 0 ? c->lanes_override : (c->n_pairs >= 384 ? 3 : c->n_pairs >= 192 ? 2 : 1);
+    if (n > sf_ctx::MAX_LANES) n = sf_ctx::MAX_LANES;
+    if (n > c->n_pairs) n = c->n_pairs;
+    return n < 1 ? 1 : n;
+}
+
+// the per-pair part of runSolver for the pairs [lo, lo + n) on `stream`; returns false when the debug stop step cut it short
+static bool enqueue_lane(sf_ctx* c, const Arena& a, cudaStream_t stream, int lo, int n_lane, int* n_out) {
     int ctr = 0;
-    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames, &ctr};
-    const Arena& a = c->a;
+    const LaunchCfg cfg{stream, n_lane, c->n_frames, &ctr};
     const DevParams& dp = c->dp;
     int n = 0;
-    c->prof.clear();
-    c->ev_used = 0;
-    { ProfScope ps(c, 0, 0); n += launch_init_pairs(a, dp, c->d_twist_in, cfg); }
-    if (build_pyramids) { ProfScope ps(c, 1, 0); n += launch_pyramids(a, c->geom, c->levels, cfg); }
+    { ProfScope ps(c, 0, 0); n += launch_init_pairs(a, dp, c->d_twist_in + 6 * (size_t)lo, cfg); }
     { ProfScope ps(c, 2, 0); n += launch_kmeans(a, dp, c->geom, c->levels, cfg); }
     bool stop = false;
     for (int i = 0; i < c->levels && !stop; i++)
@@ -410,10 +460,38 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
                 }
             { ProfScope ps(c, 7, image_level); n += launch_pose_update(a, dp, i, k, cfg); }
         }
+    { ProfScope ps(c, 8, 0); n += launch_finish(a, dp, c->geom[0], cfg); }
+    *n_out += n;
+    return !stop;
+}
+
+static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
+    int ctr = 0;
+    const LaunchCfg cfg{c->stream, c->n_pairs, c->n_frames, &ctr};
+    const Arena& a = c->a;
+    const DevParams& dp = c->dp;
+    int n = 0;
+    c->prof.clear();
+    c->ev_used = 0;
+    if (build_pyramids) { ProfScope ps(c, 1, 0); n += launch_pyramids(a, c->geom, c->levels, cfg); }
+    const int lanes = choose_lanes(c);
+    c->last_lanes = lanes;
+    bool complete = true;
+    if (lanes == 1) complete = enqueue_lane(c, a, c->stream, 0, c->n_pairs, &n);
+    else {
+        CU(cudaEventRecord(c->ev_fork, c->stream));  // the pyramids are ready
+        const int per = (c->n_pairs + lanes - 1) / lanes;
+        for (int l = 0; l < lanes; l++) {
+            const int lo = l * per, nl = std::min(per, c->n_pairs - lo);
+            if (nl <= 0) continue;
+            if (l) CU(cudaStreamWaitEvent(c->lane_stream[l], c->ev_fork, 0));
+            complete = enqueue_lane(c, lane_arena(c, l, lo), c->lane_stream[l], lo, nl, &n) && complete;
+            if (l) { CU(cudaEventRecord(c->ev_join[l], c->lane_stream[l])); CU(cudaStreamWaitEvent(c->stream, c->ev_join[l], 0)); }
+        }
+    }
     {
         ProfScope ps(c, 8, 0);
-        n += launch_finish(a, dp, c->geom[0], cfg);
-        if (c->history && c->is_sequence && !stop) n += launch_history(a, dp, c->geom[0], 0, 0, cfg);  // StaticFusion-datasets.cpp:175-177
+        if (c->history && c->is_sequence && complete) n += launch_history(a, dp, c->geom[0], 0, 0, cfg);  // StaticFusion-datasets.cpp:175-177
         n += launch_segm_image(a, c->geom[0], cfg);
     }
     c->launches = n;
@@ -425,7 +503,7 @@ static int launch_solve(sf_ctx* c, bool build_pyramids) {
     if (c->prof_on || !c->use_graph) return enqueue_solve(c, build_pyramids);  // per-kernel events need plain launches
     for (const auto& g : c->graphs)
         if (g.n_pairs == c->n_pairs && g.n_frames == c->n_frames && g.stop_step == c->stop_step && g.pyramids == (int)build_pyramids &&
-            g.history == (c->history && c->is_sequence)) {
+            g.history == (c->history && c->is_sequence) && g.lanes == choose_lanes(c)) {
             CU(cudaGraphLaunch(g.exec, c->stream));
             c->launches = g.launches;
             return SF_OK;
@@ -440,7 +518,7 @@ static int launch_solve(sf_ctx* c, bool build_pyramids) {
     const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e2 != cudaSuccess) return fail(SF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2));
-    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, (int)(c->history && c->is_sequence), exec, c->launches});
+    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, (int)(c->history && c->is_sequence), choose_lanes(c), exec, c->launches});
     CU(cudaGraphLaunch(exec, c->stream));
     return SF_OK;
 }
@@ -479,6 +557,7 @@ int sf_sync(sf_ctx* c) {
 
 uint64_t sf_stream(sf_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 int sf_last_launch_count(sf_ctx* c) { return c ? c->launches : 0; }
+int sf_last_lane_count(sf_ctx* c) { return c ? choose_lanes(c) : 0; }
 
 int sf_download_range(sf_ctx* c, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
                       uint8_t* labels_u8, int out_space, int* irls_iters, int* status, float* per_cluster_residual) {

@@ -31,7 +31,9 @@ struct Arena {
     float* warp_i;              // [F][P0]
     uint8_t* tiles;             // [F][tiles_per_pair(P0)][TILE_BYTES] raw Jacobian rows + valid-pixel labels
     float* dbg;                 // [F][NPLANES][P0] linearisation planes, only with the trace flag (else nullptr)
-    int* gcount;                // [2]: pairs active in the current step, pairs still inside the IRLS loop
+    int* gcount;                // [4]: pairs active in the current step, pairs still inside the IRLS loop, lengths of iter_list0 / iter_list1
+    int* iter_list0;            // [F] pairs that run IRLS iteration it (odd it); pass 2 of iteration it appends the pairs that go on
+    int* iter_list1;            // [F] ... to the other list (even it), so every pass launch is sized by the pairs still iterating
     int* active_list;           // [F] indices of the pairs active in the current step (first gcount[0] entries)
     int* work_ctr;              // [MAX_WORK_CTRS] dynamic item counters, one per pass launch of a solve (zeroed by init_pairs)
     PairCtl* ctl;               // [F]

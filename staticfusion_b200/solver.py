@@ -289,6 +289,11 @@ class StaticFusionSolver:
         return r
 
     @property
+    def lanes(self) -> int:
+        """Concurrent pair ranges (streams) the current batch's schedule is cut into."""
+        return int(self.L.sf_last_lane_count(self.h))
+
+    @property
     def stream(self) -> int:
         return int(self.L.sf_stream(self.h))
 
@@ -372,31 +377,44 @@ class PipelinedSolver:
         self.ctx = [StaticFusionSolver(self.params, device=device, max_batch=chunk + (self.HALO if history else 0)) for _ in range(n_ctx)]
         for c in self.ctx:
             c.set_history(history)
+        self.pending = []  # (ctx, span, result) of the chunks in flight, oldest first
+        self._turn = 0
 
     def close(self):
+        self.flush()
         for c in self.ctx:
             c.close()
 
-    def solve_sequence(self, depth, inten, out: BatchResult | None = None, want_images: bool = True) -> BatchResult:
+    def solve_sequence(self, depth, inten, out: BatchResult | None = None, want_images: bool = True, wait: bool = True) -> BatchResult:
+        """wait=False returns as soon as every chunk is enqueued: the call overlaps the next one (its uploads and solves run
+        while this one's results still travel back).  The caller keeps `depth` / `inten` unchanged and does not read the
+        result until ``wait_for(result)`` or ``flush()``."""
         n_pairs = int(depth.shape[0]) - 1
         r = out if out is not None else BatchResult(n_pairs, self.rows, self.cols, want_images)
-        want_images = r.b_perpixel is not None
         spans = [(s, min(s + self.chunk, n_pairs)) for s in range(0, n_pairs, self.chunk)]
-        L = self.ctx[0].L
-        pending = []  # (ctx, span) in flight
-
-        def drain(ctx, span):
-            s0, s1, halo = span
-            ctx.download_range(halo, s1 - s0, r, at=s0)
-
-        for k, (s0, s1) in enumerate(spans):
-            ctx = self.ctx[k % len(self.ctx)]
-            if len(pending) == len(self.ctx):  # this context is still busy with an older chunk: collect it first
-                drain(*pending.pop(0))
+        for s0, s1 in spans:
+            ctx = self.ctx[self._turn % len(self.ctx)]
+            self._turn += 1
+            while any(p[0] is ctx for p in self.pending):  # this context is still busy with an older chunk: collect up to it
+                self._drain(self.pending.pop(0))
             halo = min(self.HALO, s0) if self.history else 0
             ctx.upload_sequence(depth[s0 - halo:s1 + 1], inten[s0 - halo:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
             ctx.launch()
-            pending.append((ctx, (s0, s1, halo)))
-        while pending:
-            drain(*pending.pop(0))
+            self.pending.append((ctx, (s0, s1, halo), r))
+        if wait:
+            self.flush()
         return r
+
+    @staticmethod
+    def _drain(entry):
+        ctx, (s0, s1, halo), r = entry
+        ctx.download_range(halo, s1 - s0, r, at=s0)
+
+    def wait_for(self, result: BatchResult):
+        """Collect chunks (oldest first) until none of `result`'s is in flight."""
+        while any(p[2] is result for p in self.pending):
+            self._drain(self.pending.pop(0))
+
+    def flush(self):
+        while self.pending:
+            self._drain(self.pending.pop(0))

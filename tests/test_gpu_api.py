@@ -152,6 +152,54 @@ def test_pipelined_solver_is_bit_identical_to_one_call(gpu):
     ps.close()
 
 
+def test_overlapped_pipelined_calls(gpu):
+    """wait=False: consecutive calls overlap (uploads and solves of call k+1 run while call k drains); results are collected
+    by wait_for / flush and equal the blocking call bit for bit."""
+    d, c = frames("dynamic", 12, 240, 320)
+    p = gpu.default_params(240, 320, ctf_levels=3)
+    ps = gpu.PipelinedSolver(p, chunk=4, n_ctx=3)
+    ref = ps.solve_sequence(d, c)
+    outs = [gpu.BatchResult(11, 240, 320, True, pinned=True) for _ in range(2)]
+    prev = None
+    for k in range(5):
+        cur = ps.solve_sequence(d, c, out=outs[k % 2], wait=False)
+        if prev is not None:
+            ps.wait_for(prev)
+            assert same(ref, prev)
+            prev.T[:] = 0; prev.b_perpixel[:] = 0  # the buffer is rewritten by the call after next
+        prev = cur
+    ps.flush()
+    assert same(ref, prev) and not ps.pending
+    ps.close()
+
+
+def test_result_independent_of_lanes(gpu, monkeypatch):
+    """Large batches are cut into pair ranges that run on their own streams inside the captured graph (SF_LANES overrides
+    the automatic choice); pairs are independent and all sums are integer sums, so no bit may change - including the
+    5-frame history stage, which reads across the cut after the join."""
+    d, c = frames("dynamic", 11, 240, 320)
+    p = gpu.default_params(240, 320, ctf_levels=3)
+    res = []
+    for lanes in ("1", "3", "4"):
+        monkeypatch.setenv("SF_LANES", lanes)
+        s = gpu.StaticFusionSolver(p, max_batch=10)
+        r = s.solve_sequence(d, c, history=True)
+        assert s.lanes == int(lanes)
+        r2 = s.solve_sequence(d, c, history=True)  # graph replay
+        assert same(r, r2) and np.array_equal(r.per_cluster_residual, r2.per_cluster_residual, equal_nan=True)
+        res.append(r)
+        s.close()
+    monkeypatch.delenv("SF_LANES")
+    for r in res[1:]:
+        assert same(res[0], r) and np.array_equal(res[0].per_cluster_residual, r.per_cluster_residual, equal_nan=True)
+    assert np.isfinite(res[0].per_cluster_residual[4:]).any()
+    # the automatic choice: one lane for small batches
+    s = gpu.StaticFusionSolver(p, max_batch=10)
+    s.upload_sequence(d, c)
+    assert s.lanes == 1
+    s.close()
+
+
 def test_parameter_change_takes_effect_after_graph_capture(gpu, oracle_mod):
     """sf_set_params must invalidate the captured CUDA graphs (the drivers rewrite kb per frame,
     StaticFusion-datasets.cpp:156-165)."""
