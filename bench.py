@@ -289,40 +289,56 @@ def main():
     g = [hd.to(dev), hc.to(dev)]
     p = sf.default_params(rows, cols, ctf_levels=levels)
     s = sf.StaticFusionSolver(p, device=local_rank, max_batch=F)
-    stream = torch.cuda.ExternalStream(s.stream, device=dev)
     out = BatchResult(F, rows, cols, True, pinned=True)
 
-    def device_step():
-        s.upload_sequence(*g)  # device-to-device: frames land in the pyramids' level-0 slots
-        s.launch()
+    # N > 1: every step ends with one all-gather of the small result rows, which needs them on the host.  Two contexts take
+    # turns so that step k+1 is already running while step k's rows are downloaded and gathered (no device idle time).
+    n_dev_ctx = int(os.environ.get("SF_BENCH_CTXS", "1" if world == 1 else "2"))
+    ctxs = [s] + [sf.StaticFusionSolver(p, device=local_rank, max_batch=F) for _ in range(n_dev_ctx - 1)]
+    cfg["device_contexts"] = n_dev_ctx
+    streams = [torch.cuda.ExternalStream(x.stream, device=dev) for x in ctxs]
+
+    def device_step(ctx=s):
+        ctx.upload_sequence(*g)  # device-to-device: frames land in the pyramids' level-0 slots
+        ctx.launch()
+
+    def gather_step(ctx):
+        sharding.gather_rows(sharding.pack_rows(ctx.download(want_images=False)), F * world, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
-        device_step()
-    s.sync()
-    # --- timed region: EXACTLY K steps, device-timed on the library's stream (CUDA-graph replay of the schedule)
+    for k in range(max(a.warmup, 3)):
+        device_step(ctxs[k % len(ctxs)])
+    for x in ctxs:
+        x.sync()
+    # --- timed region: EXACTLY K steps, device-timed on the library's stream(s) (CUDA-graph replay of the schedule)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     launches = 0
     t_host0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(a.steps):
-        device_step()
-        if world > 1:  # one all-gather of the small result rows per batch
-            r_local = s.download(want_images=False)
-            sharding.gather_rows(sharding.pack_rows(r_local), F * world, device=dev)
-        launches += s.last_launch_count
-    e1.record(stream)
+    e0.record(streams[0])  # the device is idle (barrier): every stream's work starts after this timestamp
+    for k in range(a.steps):
+        cur = ctxs[k % len(ctxs)]
+        device_step(cur)
+        launches += cur.last_launch_count
+        if world > 1 and k > 0:  # one all-gather of the small result rows per batch
+            gather_step(ctxs[(k - 1) % len(ctxs)])
+    if world > 1:
+        gather_step(ctxs[(a.steps - 1) % len(ctxs)])
+    for ev, st in zip(e1, streams):
+        ev.record(st)
     barrier()
     t_host = time.perf_counter() - t_host0
     clk = clocks.stop()
-    elapsed_ms = e0.elapsed_time(e1)
+    elapsed_ms = max(e0.elapsed_time(ev) for ev in e1)
+    for x in ctxs[1:]:
+        x.close()
     res = s.download(want_images=False)
     cfg["lanes"] = s.lanes  # concurrent pair ranges inside the library's schedule (graph branches on separate streams)
     nv, it = s.step_stats()

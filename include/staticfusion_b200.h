@@ -214,6 +214,13 @@ int sf_download(sf_ctx* ctx, float* T_odometry, float* twist_old_out, float* b_s
 int sf_download_range(sf_ctx* ctx, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm,
                       float* b_perpixel, uint8_t* labels_u8, int out_space, int* irls_iters, int* status,
                       float* per_cluster_residual);
+/* Split-phase form: _begin enqueues the device->host copies behind the solve and returns at once (give it page-locked
+ * buffers), _end waits for them and fills the small per-pair arrays passed to _begin.  One download in flight per context;
+ * the next sf_upload_* / sf_launch on the context may be issued only after _end. */
+int sf_download_range_begin(sf_ctx* ctx, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm,
+                            float* b_perpixel, uint8_t* labels_u8, int out_space, int* irls_iters, int* status,
+                            float* per_cluster_residual);
+int sf_download_range_end(sf_ctx* ctx);
 /* cudaStream_t of the context as an integer handle (for CUDA-event timing by the caller). */
 uint64_t sf_stream(sf_ctx* ctx);
 /* Number of kernel launches enqueued by the last sf_launch. */

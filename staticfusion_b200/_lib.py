@@ -32,7 +32,7 @@ EXPORTS = [
     "sf_profile_enable", "sf_profile_read", "sf_profile_read_records", "sf_get_step_stats",
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
     "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
-    "sf_convert_frames", "sf_upload_sequence_raw", "sf_last_lane_count",
+    "sf_convert_frames", "sf_upload_sequence_raw", "sf_last_lane_count", "sf_download_range_begin", "sf_download_range_end",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -104,6 +104,8 @@ def lib():
     L.sf_sync.argtypes = [vp]
     L.sf_download.argtypes = [vp, fp, fp, fp, vp, vp, C.c_int, ip, ip]
     L.sf_download_range.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, vp, vp, C.c_int, ip, ip, fp]
+    L.sf_download_range_begin.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, vp, vp, C.c_int, ip, ip, fp]
+    L.sf_download_range_end.argtypes = [vp]
     L.sf_buffer_set.argtypes = [vp, C.c_int, fp, fp, fp, C.c_int]
     L.sf_buffer_push.argtypes = [vp, C.c_int]
     L.sf_compute_residuals_against_previous_image.argtypes = [vp, C.c_int]

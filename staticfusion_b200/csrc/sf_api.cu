@@ -48,7 +48,9 @@ struct sf_ctx {
     std::vector<float> h_cur_d, h_cur_i, h_pred_d, h_pred_i;
     bool have_cur = false, have_pred = false, trio_pyr_pred = false;
     float h_twist_old[6] = {0, 0, 0, 0, 0, 0};
-    std::vector<PairOut> h_out;
+    PairOut* h_out = nullptr;  // page-locked staging of the result rows (max_batch entries): device->host copies stay asynchronous
+    float* h_pcar = nullptr;   // page-locked staging of perClusterAverageResidual (a copy into pageable memory would block the host)
+    struct PendingDownload { bool on = false; int n = 0; float *T = nullptr, *twist = nullptr, *b_segm = nullptr; int *iters = nullptr, *status = nullptr; float* pcar = nullptr; } dl;
     std::vector<int> h_ci, h_pi;  // pair -> frame tables staged for async upload (must outlive the copy)
     // profiling: one event pair per kernel group of the last launch
     bool prof_on = false;
@@ -298,7 +300,8 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
     sf::prepare_kernels();
-    c->h_out.resize(F);
+    if (cudaHostAlloc((void**)&c->h_out, sizeof(PairOut) * F, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->h_pcar, sizeof(float) * NC * F, cudaHostAllocDefault) != cudaSuccess) { sf_destroy(c); return fail(SF_E_NOMEM, "cudaHostAlloc failed"); }
     *out = c;
     return SF_OK;
 }
@@ -314,6 +317,8 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt); cudaFree(c->d_cvt);
     drop_graphs(c);
     cudaFree(c->d_lane_gcount); cudaFree(c->d_lane_work_ctr); cudaFree(c->d_iter_list);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_pcar) cudaFreeHost(c->h_pcar);
     for (int l = 1; l < sf_ctx::MAX_LANES; l++) { if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -559,31 +564,51 @@ uint64_t sf_stream(sf_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 int sf_last_launch_count(sf_ctx* c) { return c ? c->launches : 0; }
 int sf_last_lane_count(sf_ctx* c) { return c ? choose_lanes(c) : 0; }
 
-int sf_download_range(sf_ctx* c, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
-                      uint8_t* labels_u8, int out_space, int* irls_iters, int* status, float* per_cluster_residual) {
+// split phase: _begin enqueues every device->host copy behind the solve (no host wait), _end waits and unpacks the rows
+int sf_download_range_begin(sf_ctx* c, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
+                            uint8_t* labels_u8, int out_space, int* irls_iters, int* status, float* per_cluster_residual) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    if (c->dl.on) return fail(SF_E_STATE, "a download is already in flight: call sf_download_range_end first");
     if (first_pair < 0 || n < 0 || first_pair + n > c->n_pairs) return fail(SF_E_INVALID, "pair range outside the last solve");
+    c->dl = {true, n, T_odometry, twist_old_out, b_segm, irls_iters, status, per_cluster_residual};
     if (n == 0) return SF_OK;
     CU(cudaSetDevice(c->device));
     const Arena& a = c->a;
-    CU(cudaMemcpyAsync(c->h_out.data(), a.out + first_pair, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_out, a.out + first_pair, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
     const cudaMemcpyKind kind = (out_space == SF_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, a.b_perpixel + (size_t)first_pair * a.P0, sizeof(float) * a.P0 * n, kind, c->stream));
     if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, a.P0, a.labels + (size_t)first_pair * a.pyr_stride, a.pyr_stride, a.P0, (size_t)n, kind, c->stream));
-    if (per_cluster_residual) CU(cudaMemcpyAsync(per_cluster_residual, a.pcar + (size_t)first_pair * NC, sizeof(float) * NC * n, cudaMemcpyDeviceToHost, c->stream));
+    if (per_cluster_residual) CU(cudaMemcpyAsync(c->h_pcar, a.pcar + (size_t)first_pair * NC, sizeof(float) * NC * n, cudaMemcpyDeviceToHost, c->stream));
+    return SF_OK;
+}
+
+int sf_download_range_end(sf_ctx* c) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    if (!c->dl.on) return fail(SF_E_STATE, "no download in flight");
+    const sf_ctx::PendingDownload d = c->dl;
+    c->dl.on = false;
     CU(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < n; k++) {
+    if (d.pcar && d.n) std::memcpy(d.pcar, c->h_pcar, sizeof(float) * NC * d.n);
+    for (int k = 0; k < d.n; k++) {
         const PairOut& o = c->h_out[k];
-        if (T_odometry)
+        if (d.T)
             for (int r = 0; r < 4; r++)
-                for (int q = 0; q < 4; q++) T_odometry[k * 16 + q * 4 + r] = o.T[r * 4 + q];  // row-major -> Eigen column-major
-        if (twist_old_out) std::memcpy(twist_old_out + k * 6, o.twist_old, sizeof(float) * 6);
-        if (b_segm) std::memcpy(b_segm + k * NC, o.b_segm, sizeof(float) * NC);
-        if (irls_iters) irls_iters[k] = o.irls_iters;
-        if (status) status[k] = o.status;
+                for (int q = 0; q < 4; q++) d.T[k * 16 + q * 4 + r] = o.T[r * 4 + q];  // row-major -> Eigen column-major
+        if (d.twist) std::memcpy(d.twist + k * 6, o.twist_old, sizeof(float) * 6);
+        if (d.b_segm) std::memcpy(d.b_segm + k * NC, o.b_segm, sizeof(float) * NC);
+        if (d.iters) d.iters[k] = o.irls_iters;
+        if (d.status) d.status[k] = o.status;
     }
     return SF_OK;
+}
+
+int sf_download_range(sf_ctx* c, int first_pair, int n, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel,
+                      uint8_t* labels_u8, int out_space, int* irls_iters, int* status, float* per_cluster_residual) {
+    const int rc = sf_download_range_begin(c, first_pair, n, T_odometry, twist_old_out, b_segm, b_perpixel, labels_u8, out_space, irls_iters,
+                                           status, per_cluster_residual);
+    if (rc) return rc;
+    return sf_download_range_end(c);
 }
 
 int sf_download(sf_ctx* c, float* T_odometry, float* twist_old_out, float* b_segm, float* b_perpixel, uint8_t* labels_u8,

@@ -259,6 +259,21 @@ class StaticFusionSolver:
             r.b_perpixel[sl].ctypes.data if want_images else None, r.labels[sl].ctypes.data if want_images else None, MEM_HOST,
             _ip(r.irls_iters[sl]), _ip(r.status[sl]), _fp(r.per_cluster_residual[sl])))
 
+    def download_range_begin(self, first: int, n: int, r: BatchResult, at: int = 0):
+        """Enqueue the copies of download_range behind the solve (no host wait); finish with download_range_end()."""
+        want_images = r.b_perpixel is not None
+        sl = slice(at, at + n)
+        self._dl_keep = [r.T[sl], r.twist_old[sl], r.b_segm[sl], r.irls_iters[sl], r.status[sl], r.per_cluster_residual[sl]]  # views stay alive
+        k = self._dl_keep
+        check(self.L.sf_download_range_begin(
+            self.h, int(first), int(n), _fp(k[0]), _fp(k[1]), _fp(k[2]),
+            r.b_perpixel[sl].ctypes.data if want_images else None, r.labels[sl].ctypes.data if want_images else None, MEM_HOST,
+            _ip(k[3]), _ip(k[4]), _fp(k[5])))
+
+    def download_range_end(self):
+        check(self.L.sf_download_range_end(self.h))
+        self._dl_keep = None
+
     # ---- split phase (benchmark) ----
     def upload_pairs(self, depth_cur, inten_cur, depth_pred, inten_pred, twist_old=None):
         n = int(depth_cur.shape[0])
@@ -400,6 +415,7 @@ class PipelinedSolver:
             halo = min(self.HALO, s0) if self.history else 0
             ctx.upload_sequence(depth[s0 - halo:s1 + 1], inten[s0 - halo:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
             ctx.launch()
+            ctx.download_range_begin(halo, s1 - s0, r, at=s0)  # the results start back as soon as the chunk is solved
             self.pending.append((ctx, (s0, s1, halo), r))
         if wait:
             self.flush()
@@ -407,8 +423,8 @@ class PipelinedSolver:
 
     @staticmethod
     def _drain(entry):
-        ctx, (s0, s1, halo), r = entry
-        ctx.download_range(halo, s1 - s0, r, at=s0)
+        ctx, _, _ = entry
+        ctx.download_range_end()
 
     def wait_for(self, result: BatchResult):
         """Collect chunks (oldest first) until none of `result`'s is in flight."""

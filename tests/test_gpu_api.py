@@ -76,6 +76,18 @@ def test_call_order_errors(gpu):
     with pytest.raises(gpu.SfError) as e:
         s.solve_sequence(d, c)  # 2 pairs > max_batch
     assert e.value.code == -1
+    # split-phase download: one in flight per context, _end needs a _begin
+    with pytest.raises(gpu.SfError) as e:
+        s.download_range_end()
+    assert e.value.code == -4
+    r = s.solve_sequence(d[:2], c[:2])
+    r2 = gpu.BatchResult(1, 240, 320, True)
+    s.download_range_begin(0, 1, r2)
+    with pytest.raises(gpu.SfError) as e:
+        s.download_range_begin(0, 1, r2)
+    assert e.value.code == -4
+    s.download_range_end()
+    assert same(r, r2)
     s.close()
 
 
