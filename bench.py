@@ -363,7 +363,10 @@ def main():
     s.close()
     del g
     torch.cuda.empty_cache()
-    ps = sf.PipelinedSolver(p, device=local_rank, chunk=min(128, F), n_ctx=3)
+    # shape of the pipeline (pairs per chunk x contexts): measured with scripts/exp_e2e.py, 256 x 3 is the fastest for QVGA
+    e2e_chunk, e2e_ctx = (int(v) for v in os.environ.get("SF_BENCH_E2E", "256x3").split("x"))
+    e2e_chunk = min(e2e_chunk, F)
+    ps = sf.PipelinedSolver(p, device=local_rank, chunk=e2e_chunk, n_ctx=e2e_ctx)
     e2e_in_bytes = int(hd.numel() * 4 + hc.numel() * 4)
 
     outs = [out, BatchResult(F, rows, cols, True, pinned=True)]  # double-buffered results: step k+1 is enqueued while step k drains
@@ -472,7 +475,7 @@ def main():
                 "e2e": {"value": eq_total * a.steps / e2e_s, "unit": unit, "frames_per_s": F * world * a.steps / e2e_s,
                         "h2d_bytes_per_step": int(e2e_in_bytes),
                         "d2h_bytes_per_step": int(F * (rows * cols * 5 + 200)),
-                        "timing": "host wall clock around K PipelinedSolver.solve_sequence calls (3 contexts x 128-pair chunks, pinned buffers, "
+                        "timing": f"host wall clock around K PipelinedSolver.solve_sequence calls ({e2e_ctx} contexts x {e2e_chunk}-pair chunks, pinned buffers, "
                                   "double-buffered results: step k+1 is enqueued while step k's results travel back; every step's inputs go "
                                   "host->device and every step's poses / weights / labels come back inside the timed region)",
                         "matches_device_run_bitwise": e2e_ok},
