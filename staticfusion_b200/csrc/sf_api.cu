@@ -204,6 +204,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
         g.disp_u = 0.5f * float(g.cols - 1);
         g.disp_v = 0.5f * float(g.rows - 1);
         g.off = off;
+        g.cols_magic = (unsigned)((0x100000000ull + (unsigned long long)g.cols - 1ull) / (unsigned long long)g.cols);
         off += (size_t)g.P;
     }
     Arena& a = c->a;

@@ -58,7 +58,18 @@ struct LevelGeom {
     float inv_f_warp;       // 1.f/f                            FrontEnd.cpp:874
     float disp_u, disp_v;   // 0.5f*(cols-1), 0.5f*(rows-1)
     size_t off;             // offset (pixels) of this level inside a per-image pyramid
+    unsigned cols_magic;    // ceil(2^32 / cols): pixel index -> (row, column) without an integer division
 };
+
+// row and column of pixel p of a level: p / cols == umulhi(p, ceil(2^32 / cols)) while p * cols < 2^32 (any level up to
+// 2048 x 2048); the correction steps make the result right for every non-negative p anyway
+__device__ __forceinline__ void split_rc(int p, const LevelGeom& g, int& row, int& col) {
+    int q = (int)__umulhi((unsigned)p, g.cols_magic);
+    int r = p - q * g.cols;
+    if (r < 0) { q--; r += g.cols; }
+    if (r >= g.cols) { q++; r -= g.cols; }
+    row = q; col = r;
+}
 
 // solver tunables as the kernels see them
 struct DevParams {
