@@ -455,6 +455,9 @@ def main():
             tj = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json")))
             if tj.get("config") == a.config:
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+                if "algorithmic_bytes_of_that_launch" in tj:  # the captured launch is the fullest one, not the average one
+                    detail["traffic_launch"] = {"algorithmic_bytes": tj["algorithmic_bytes_of_that_launch"], "dram_bytes": traffic,
+                                                "dram_over_algorithmic": traffic / tj["algorithmic_bytes_of_that_launch"]}
         except (OSError, KeyError, ValueError):
             pass
         roof = {"bound": "hbm", "kernel": "irls_pass1_kernel (finest level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
