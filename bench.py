@@ -365,7 +365,7 @@ def main():
     torch.cuda.empty_cache()
     # shape of the pipeline (pairs per chunk x contexts): measured with scripts/exp_e2e.py, 256 x 3 is the fastest for QVGA
     e2e_chunk, e2e_ctx = (int(v) for v in os.environ.get("SF_BENCH_E2E", "256x3").split("x"))
-    e2e_chunk = min(e2e_chunk, F)
+    e2e_chunk = max(1, min(e2e_chunk, (F + 1) // 2))  # at least two chunks per step, so that a step's copies overlap its own solves
     ps = sf.PipelinedSolver(p, device=local_rank, chunk=e2e_chunk, n_ctx=e2e_ctx)
     e2e_in_bytes = int(hd.numel() * 4 + hc.numel() * 4)
 
