@@ -74,3 +74,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not pat.search(txt), (dirpath, f, pat.search(txt).group(0))
+
+
+def test_division_free_pixel_split_is_exact():
+    """sf_device.cuh split_rc: p / cols == (p * ceil(2^32 / cols)) >> 32 for every pixel of every level width the library
+    accepts (cols % 4 == 0, up to 2048 x 2048), so its correction steps never fire."""
+    import numpy as np
+
+    for cols in (20, 40, 80, 160, 320, 640, 1280, 2048, 100, 36, 1000):
+        magic = (2**32 + cols - 1) // cols
+        assert magic < 2**32
+        p = np.arange(0, min(cols * 2048, 2**22), dtype=np.uint64)
+        q = (p * np.uint64(magic)) >> np.uint64(32)
+        assert np.array_equal(q, p // np.uint64(cols)), cols
