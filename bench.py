@@ -15,8 +15,9 @@ reference StaticFusion-datasets.cpp:171-180) over one batch of synthetic frame p
 * roofline: the dominant kernel (irls_pass1 at the finest level), algorithmic bytes (48 B per valid pixel
             per pass = half of SURVEY §8d's 96*N per iteration) over its CUDA-event time, against the
             measured HBM peak in MEASURED_PEAKS.json.
-* cpu_baseline / --impl reference: the CPU oracle (a port: the reference itself cannot be built here)
-  timed on the box's host cores on a bounded sample of the same workload.
+* cpu_baseline / --impl reference: the CPU oracle's reference-literal policy (a plain-loop port that is pinned bit for bit
+  against the reference's own sources compiled with a header shim) timed on the box's host cores on a
+  bounded sample of the same workload.
 
 N > 1: launched by torchrun, one rank per GPU, frame pairs sharded (no data-path collective), one NCCL
 all-gather of the 48-float result rows per batch; weak scaling (per-GPU batch fixed).
