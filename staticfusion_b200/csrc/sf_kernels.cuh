@@ -1,4 +1,4 @@
-// sf_kernels.cuh — launch interface between the C ABI (sf_api.cu) and the kernels (sf_kernels.cu).
+// sf_kernels.cuh — launch interface between the C ABI (sf_api.cu) and the kernels (sf_k_*.cu).
 #pragma once
 #include "sf_device.cuh"
 
