@@ -59,20 +59,27 @@ inline float sq(float x) { return x * x; }
 inline int64_t fixq(float x, int s) { return (int64_t)llrintf(ldexpf(x, s)); }
 inline double fixval(int64_t acc, int s) { return std::ldexp((double)acc, -s); }
 
-/* EXACT policy for the normal equations and |res|^2: every column of the weighted system is scaled by a
- * power of two so that its magnitude stays below 2^10, each product is rounded to the nearest integer
- * (round-half-even of the exact product, which is what fmaf(a, b, 1.5*2^23) - 1.5*2^23 yields on the GPU)
- * and the integers are summed: associative, hence independent of the reduction order. */
+/* EXACT policy for the normal equations and |res|^2 (mirrors sf_device.cuh): every column of the weighted system is
+ * scaled by a power of two so that its magnitude stays below 2^10; each product of two scaled entries (exact in double:
+ * 24 x 24 bits) is rounded ONCE to the nearest multiple of 2^-20 (round-half-even) and those fixed-point values are summed
+ * exactly as integers: associative, hence independent of the reduction order.  On the GPU the rounding and the addition
+ * are one double-precision FMA onto an accumulator that stays inside the binade of 1.5 * 2^32 (its ulp is 2^-20 there, so
+ * fma(a, b, acc) == acc + round_to_2^-20(a * b) exactly); here it is nearbyint + an integer sum.  The quantum is 2^-40 of
+ * (column bound x column bound), which puts the sums ~1e-9 (relative) from plain double sums at every pyramid level
+ * (scripts/sweep_numerics.py; the first-round policy rounded each product to 2^-20 of that bound). */
+constexpr int ORC_QSCALE_BITS = 10; /* scaled columns stay below 2^10 */
+constexpr int ORC_QFRAC_BITS = 20;  /* products are rounded to multiples of 2^-20 */
+constexpr int ORC_LABEL_BITS = 30;  /* per-label residual terms: round(x * 2^s) < 2^30 (cvt.rni.s32.f32 on the GPU) */
 inline int scale_exponent(float bound) {
     if (!(bound > 0.f) || !std::isfinite(bound)) return 0;
     int e;
     (void)frexpf(bound, &e); /* bound = m * 2^e, m in [0.5, 1) */
-    int s = 10 - e;
+    int s = ORC_QSCALE_BITS - e;
     if (s > 100) s = 100;
     if (s < -100) s = -100;
     return s;
 }
-inline int64_t qprod(float a, float b) { return (int64_t)std::nearbyint((double)a * (double)b); }
+inline int64_t qprod(float a, float b) { return (int64_t)std::nearbyint(std::ldexp((double)a * (double)b, ORC_QFRAC_BITS)); }
 
 /* =====================================================================================
  * Small dense algebra (templated on float / double)
@@ -1138,7 +1145,7 @@ void orc_ctx::solveOdometryAndSegmJoint() {
                     for (int i = 0; i < 6; i++) {
                         for (int j = i; j < 6; j++) {
                             const int64_t q = qprod(aws[i], aws[j]);
-                            if (q > 2097152 || q < -2097152) status |= 8; /* scale bound violated: must never happen */
+                            if (q > ((int64_t)1 << (2 * ORC_QSCALE_BITS + ORC_QFRAC_BITS)) || q < -((int64_t)1 << (2 * ORC_QSCALE_BITS + ORC_QFRAC_BITS))) status |= 8; /* scale bound violated: must never happen */
                             AtAq[i * 6 + j] += q;
                         }
                         AtBq[i] += qprod(aws[i], bws);
@@ -1162,8 +1169,8 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         }
         if (quant) {
             for (int i = 0; i < 6; i++) {
-                for (int j = i; j < 6; j++) AtA[i * 6 + j] = std::ldexp((double)AtAq[i * 6 + j], -(sexp[i] + sexp[j]));
-                AtB[i] = std::ldexp((double)AtBq[i], -(sexp[i] + sexp[6]));
+                for (int j = i; j < 6; j++) AtA[i * 6 + j] = std::ldexp((double)AtAq[i * 6 + j], -(sexp[i] + sexp[j]) - ORC_QFRAC_BITS);
+                AtB[i] = std::ldexp((double)AtBq[i], -(sexp[i] + sexp[6]) - ORC_QFRAC_BITS);
             }
         }
         for (int i = 0; i < 6; i++)
@@ -1205,15 +1212,16 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         const float aver_res_old = aver_res;
         double rs_d = 0; float rs_f = 0.f;
         /* EXACT: |res| <= |B| + sum_k |Var_k| |A_k| bounds the residuals; same power-of-two scaling as above */
-        int rexp = 0; int64_t rs_q = 0;
+        int rexp = 0, lexp = 0; int64_t rs_q = 0;
         if (quant) {
             float rb = colbound[6];
             for (int c = 0; c < 6; c++) rb += std::fabs(Var[c]) * colbound[c];
             rexp = scale_exponent(rb);
+            lexp = rexp + (ORC_LABEL_BITS - ORC_QSCALE_BITS - 1); /* |res_c| + |res_d| < 2^(11 - rexp): the scaled term stays below 2^30 */
         }
         for (size_t n = 0; n < N; n++) {
             const float ress_here = std::fabs(res[2 * n]) + std::fabs(res[2 * n + 1]);
-            if (quant) fix_label[lab[n]] += (int64_t)std::nearbyint((double)ress_here * std::ldexp(1.0, rexp + 9));
+            if (quant) fix_label[lab[n]] += (int64_t)llrintf(ldexpf(ress_here, lexp)); /* cvt.rni.s32.f32 of the scaled term on the GPU */
             else if (exact) fix_label[lab[n]] += fixq(ress_here, 30);
             else aver_res_label[lab[n]] += ress_here;
             num_pix_label[lab[n]]++;
@@ -1225,10 +1233,10 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         }
         if (exact) {
             int64_t tot = 0;
-            const int ls = quant ? rexp + 9 : 30; /* EXACT: |res_c|+|res_d| < 2^(11-rexp), so the scaled term stays below 2^20 */
+            const int ls = quant ? lexp : 30;
             for (int l = 0; l < NC; l++) { tot += fix_label[l]; aver_res_label[l] = (float)fixval(fix_label[l], ls); }
             aver_res = (float)fixval(tot, ls) / float(2 * N);
-            res_sq = quant ? std::ldexp((double)rs_q, -2 * rexp) : rs_d;
+            res_sq = quant ? std::ldexp((double)rs_q, -2 * rexp - ORC_QFRAC_BITS) : rs_d;
         } else {
             float tot = 0.f;
             for (int l = 0; l < NC; l++) tot += aver_res_label[l];

@@ -191,6 +191,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     if (!c) return fail(SF_E_NOMEM, "host allocation failed");
     c->p = *p; c->device = device; c->max_batch = max_batch; c->flags = flags; c->levels = p->ctf_levels;
     if (const char* e = std::getenv("SF_FUSED_MAX_TILES")) c->fused_max_tiles = std::atoi(e);  // tuning / A-B measurements
+    c->fused_max_tiles = std::min(c->fused_max_tiles, 4 * MAX_TILES_PER_WARP_ITEM);  // the fused kernel's smallest block has 4 warps
     fill_dev_params(c);
     // level geometry, constants evaluated exactly as the reference does (FrontEnd.cpp:378-380, 537, 778-780, 874)
     size_t off = 0;

@@ -44,11 +44,18 @@ constexpr int FIX_WARP_I = 22;  // warp intensity accumulator, packed with the 2
 constexpr int FIX_PRIOR = 32;   // seg prior sum (SegmentationBackground.cpp:75)
 constexpr int FIX_ABSB = 32;    // sum w|dt| for the initial mean residual (FrontEnd.cpp:590)
 constexpr int FIX_RES = 30;     // per-label residual sums (FrontEnd.cpp:661)
-// normal equations and |res|^2: columns scaled by powers of two below 2^QSCALE_BITS, products rounded to
-// integers with the 1.5*2^23 trick and summed as integers (associative -> any reduction order, bit-reproducible)
+// normal equations and |res|^2: columns scaled by powers of two below 2^QSCALE_BITS; the product of two scaled entries
+// (exact in double) is rounded ONCE to a multiple of 2^-QFRAC_BITS and added, both inside one double-precision FMA onto an
+// accumulator that stays in the binade of QMAGIC_D = 1.5 * 2^32: the ulp there is 2^-20, so fma(a, b, acc) ==
+// acc + round_to_2^-20(a * b) exactly.  The accumulator's bit pattern minus QMAGIC_D's is the fixed-point sum as an integer;
+// integer addition is associative -> any thread / block / GPU partition gives the same bits.  A thread may add at most
+// 2^11 products (< 2^20 each) before its accumulator could leave the binade: MAX_TILES_PER_WARP_ITEM tiles (4 rows per lane).
 constexpr int QSCALE_BITS = 10;
-constexpr float QMAGIC = 12582912.f;          // 1.5 * 2^23
-constexpr unsigned QMAGIC_BITS = 0x4B400000u;  // bit pattern of QMAGIC
+constexpr int QFRAC_BITS = 20;
+constexpr double QMAGIC_D = 6442450944.0;                  // 1.5 * 2^32
+constexpr long long QMAGIC_D_BITS = 0x41F8000000000000ll;  // its bit pattern
+constexpr int MAX_TILES_PER_WARP_ITEM = 256;               // 1024 rows per thread: half the binade's head-room
+constexpr int LABEL_BITS = 30;  // per-label residual terms: round(x * 2^s) < 2^30 (one cvt.rni.s32.f32), summed as two 16-bit limbs
 
 // geometry of one pyramid level (host computes the float constants exactly as the reference does)
 struct LevelGeom {

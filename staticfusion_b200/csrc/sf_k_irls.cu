@@ -16,10 +16,11 @@ namespace sf {
 //   res   = m * (-b_raw + sum_k Var_k * a_raw_k)                         (:644-646 on the raw row, then normalised)
 //   w     = clamp(b_segm)/sqrt(1 + (res/(kc*aver_res))^2)                (:624-633)
 //   aw_k  = (w * (m * 2^s_k)) * a_raw_k                                  (:628, scaled by the column's power of two)
-// Normal equations as INTEGER sums: a product of two scaled entries is rounded to the nearest integer by adding
-// 1.5*2^23 inside one fused multiply-add (exact product, one rounding, ties to even) and the float's bit pattern is
-// accumulated with integer adds.  Integer addition is associative, so the sums are bit-reproducible for any
-// thread / block / GPU partition.
+// Normal equations as order-independent FIXED-POINT sums: the product of two scaled entries is exact in double; one
+// double-precision FMA rounds it to a multiple of 2^-20 (ties to even) and adds it to an accumulator that stays inside the
+// binade of 1.5 * 2^32, whose ulp is 2^-20 -- so every addition is exact and the accumulator's bit pattern, minus the
+// constant's, is the integer sum of the rounded products.  Integer addition is associative, so the sums are
+// bit-reproducible for any thread / block / GPU partition (sf_device.cuh).
 __device__ __forceinline__ float residual_raw(const float* a, float b, const float* var) {
     float r = -b;
 #pragma unroll
@@ -27,12 +28,18 @@ __device__ __forceinline__ float residual_raw(const float* a, float b, const flo
     return r;
 }
 
-// exact warp sum of per-thread int32 partials without overflow: low and high halves are reduced separately
-__device__ __forceinline__ long long warp_sum_i32_exact(int v) {
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
-    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-    return (long long)hi * 65536ll + (long long)lo;
+// exact warp sum of per-thread int64 partials (|sum| < 2^63): four 16-bit limbs, one REDUX each
+__device__ __forceinline__ long long warp_sum_i64_exact(long long v) {
+    const unsigned lo = (unsigned)v;
+    const int hi = (int)(v >> 32);
+    const unsigned l0 = __reduce_add_sync(0xffffffffu, lo & 0xffffu);
+    const unsigned l1 = __reduce_add_sync(0xffffffffu, lo >> 16);
+    const unsigned h0 = __reduce_add_sync(0xffffffffu, (unsigned)hi & 0xffffu);
+    const int h1 = __reduce_add_sync(0xffffffffu, hi >> 16);
+    return (long long)h1 * 281474976710656ll + ((long long)h0 << 32) + ((long long)l1 << 16) + (long long)l0;
 }
+// the integer a fixed-point accumulator holds
+__device__ __forceinline__ long long fixacc_value(double acc) { return __double_as_longlong(acc) - QMAGIC_D_BITS; }
 
 // ---- TMA bulk-copy pipeline -----------------------------------------------------------------------------------
 // Every warp owns a ring of PS_STAGES tile buffers in shared memory.  Lane 0 arms the stage's mbarrier with the tile
@@ -40,10 +47,10 @@ __device__ __forceinline__ long long warp_sum_i32_exact(int v) {
 // the tile with conflict-free 8-byte shared loads (lane = 2 pixels) and refills the stage.  No block-wide
 // synchronisation in the streaming loop; two blocks of 8 warps per SM keep 48 tiles (175 KB) in flight.
 #ifndef SF_PS_WARPS
-#define SF_PS_WARPS 12
+#define SF_PS_WARPS 8
 #endif
 #ifndef SF_PS_STAGES
-#define SF_PS_STAGES 2
+#define SF_PS_STAGES 3
 #endif
 constexpr int PS_WARPS = SF_PS_WARPS;
 constexpr int PS_STAGES = SF_PS_STAGES;
@@ -116,65 +123,60 @@ __device__ __forceinline__ PassRing pass_ring_setup(unsigned char* dyn_smem, int
 constexpr size_t PS_DYN_SMEM = PS_RING_BYTES + PS_WARPS * PS_STAGES * sizeof(unsigned long long);
 
 // ---- per-tile bodies shared by the multi-block passes and the fused per-pair kernel -------------------------------
-// pass 1 on one tile: robust weights (:615-637) and the integer normal equations (:640-641) of 2 pixels per lane
+// A lane takes the pixels `lane` and `lane + 32` of the tile: conflict-free 4-byte shared loads, 32 consecutive pixels of
+// an image row per step (labels are spatially coherent, so pass 2's label groups are few).
+// pass 1 on one tile: robust weights (:615-637) and the fixed-point normal equations (:640-641) of 2 pixels per lane
 __device__ __forceinline__ void pass1_tile(const unsigned char* tile, int lane, int it, float inv_max_c, float inv_max_d,
                                            float inv_c_Cauchy, const float* s_b, const float* var, const float* mc, const float* md,
-                                           unsigned (&acc)[27]) {
+                                           double (&acc)[27]) {
     const float* tr = reinterpret_cast<const float*>(tile);
-    const uchar2 vl2 = *reinterpret_cast<const uchar2*>(tile + TILE_ROW_BYTES + 2 * lane);
-    float2 v[NROWPL];
-#pragma unroll
-    for (int k = 0; k < NROWPL; k++) v[k] = *reinterpret_cast<const float2*>(tr + k * ROW_TILE + 2 * lane);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
+        const int px = lane + 32 * j;
         // invalid pixels carry zero rows (linearise_kernel) and get a zero weight: no branch, they add exactly 0
-        const int vl = j ? vl2.y : vl2.x;
-        float ac[7], ad[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) { ac[k] = j ? v[RW_AC + k].y : v[RW_AC + k].x; ad[k] = j ? v[RW_AD + k].y : v[RW_AD + k].x; }
-        // res = -B before the first solve (:589), else A*Var - B (:644-646)
-        const float res_c = inv_max_c * ((it == 1) ? -ac[6] : residual_raw(ac, ac[6], var));
-        const float res_d = inv_max_d * ((it == 1) ? -ad[6] : residual_raw(ad, ad[6], var));
+        const int vl = tile[TILE_ROW_BYTES + px];
         const float bw = (vl < NC) ? s_b[vl] : 0.f;
-        const float w_c = bw * sqrt_rn_normal(rcp_rn_normal(1.f + sq(res_c * inv_c_Cauchy)));  // :627
-        const float w_d = bw * sqrt_rn_normal(rcp_rn_normal(1.f + sq(res_d * inv_c_Cauchy)));  // :633
 #pragma unroll
-        for (int k = 0; k < 7; k++) { ac[k] = (w_c * mc[k]) * ac[k]; ad[k] = (w_d * md[k]) * ad[k]; }
-        int q = 0;
+        for (int r = 0; r < 2; r++) {  // colour row, depth row
+            float a[7];
 #pragma unroll
-        for (int ii = 0; ii < 6; ii++)
+            for (int k = 0; k < 7; k++) a[k] = tr[((r ? RW_AD : RW_AC) + k) * ROW_TILE + px];
+            // res = -B before the first solve (:589), else A*Var - B (:644-646)
+            const float res = (r ? inv_max_d : inv_max_c) * ((it == 1) ? -a[6] : residual_raw(a, a[6], var));
+            const float w = bw * sqrt_rn_normal(rcp_rn_normal(1.f + sq(res * inv_c_Cauchy)));  // :627, :633
+            double d[7];
 #pragma unroll
-            for (int jj = ii; jj < 6; jj++) {  // one 3-input integer add takes the colour and the depth term
-                acc[q] += __float_as_uint(fmaf(ac[ii], ac[jj], QMAGIC)) + __float_as_uint(fmaf(ad[ii], ad[jj], QMAGIC));
-                q++;
-            }
+            for (int k = 0; k < 7; k++) d[k] = (double)((w * (r ? md[k] : mc[k])) * a[k]);
+            int q = 0;
 #pragma unroll
-        for (int ii = 0; ii < 6; ii++)
-            acc[21 + ii] += __float_as_uint(fmaf(ac[ii], ac[6], QMAGIC)) + __float_as_uint(fmaf(ad[ii], ad[6], QMAGIC));
+            for (int ii = 0; ii < 6; ii++)
+#pragma unroll
+                for (int jj = ii; jj < 6; jj++) { acc[q] = fma(d[ii], d[jj], acc[q]); q++; }
+#pragma unroll
+            for (int ii = 0; ii < 6; ii++) acc[21 + ii] = fma(d[ii], d[6], acc[21 + ii]);
+        }
     }
 }
 
 // pass 2 on one tile: residuals of the new solution (:644-646), |res|^2 and the per-label sums (:650-667)
 __device__ __forceinline__ void pass2_tile(const unsigned char* tile, int lane, float inv_max_c, float inv_max_d, const float (&var)[6],
-                                           float rscale, float lscale, int* fix_w, int* cnt_w, unsigned& rs) {
+                                           float rscale, float lscale, long long* fix_w, int* cnt_w, double& rs) {
     const float* tr = reinterpret_cast<const float*>(tile);
-    const uchar2 vl2 = *reinterpret_cast<const uchar2*>(tile + TILE_ROW_BYTES + 2 * lane);
-    float2 v[NROWPL];
-#pragma unroll
-    for (int k = 0; k < NROWPL; k++) v[k] = *reinterpret_cast<const float2*>(tr + k * ROW_TILE + 2 * lane);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-        const int vl = j ? vl2.y : vl2.x;
+        const int px = lane + 32 * j;
+        const int vl = tile[TILE_ROW_BYTES + px];
         const bool on = vl < NC;  // invalid pixels carry zero rows: their residual is 0
         float ac[7], ad[7];
 #pragma unroll
-        for (int k = 0; k < 7; k++) { ac[k] = j ? v[RW_AC + k].y : v[RW_AC + k].x; ad[k] = j ? v[RW_AD + k].y : v[RW_AD + k].x; }
+        for (int k = 0; k < 7; k++) { ac[k] = tr[(RW_AC + k) * ROW_TILE + px]; ad[k] = tr[(RW_AD + k) * ROW_TILE + px]; }
         const float res_c = inv_max_c * residual_raw(ac, ac[6], var);
         const float res_d = inv_max_d * residual_raw(ad, ad[6], var);
         const float ress_here = fabsf(res_c) + fabsf(res_d);  // :660
-        const float rc_s = res_c * rscale, rd_s = res_d * rscale;
-        rs += __float_as_uint(fmaf(rc_s, rc_s, QMAGIC)) + __float_as_uint(fmaf(rd_s, rd_s, QMAGIC));
-        const int q = (int)(__float_as_uint(fmaf(ress_here, lscale, QMAGIC)) - QMAGIC_BITS);  // round(ress * 2^(rexp+9))
+        const double rc_s = (double)(res_c * rscale), rd_s = (double)(res_d * rscale);
+        rs = fma(rc_s, rc_s, rs);
+        rs = fma(rd_s, rd_s, rs);
+        const unsigned q = (unsigned)__float2int_rn(ress_here * lscale);  // round(ress * 2^(rexp+19)) < 2^30
         // per-label sums: lanes are grouped by label (1-3 groups per warp), one REDUX per group
         unsigned todo = __ballot_sync(0xffffffffu, on);
         while (todo) {
@@ -182,8 +184,9 @@ __device__ __forceinline__ void pass2_tile(const unsigned char* tile, int lane, 
             const int l = __shfl_sync(0xffffffffu, vl, leader);
             const bool mine = on && (vl == l);
             const unsigned grp = __ballot_sync(0xffffffffu, mine);
-            const int sum = __reduce_add_sync(0xffffffffu, mine ? q : 0);
-            if (lane == leader) { fix_w[l] += sum; cnt_w[l] += __popc(grp); }
+            const unsigned lo = __reduce_add_sync(0xffffffffu, mine ? (q & 0xffffu) : 0u);  // 32 terms < 2^30: two exact limbs
+            const unsigned hi = __reduce_add_sync(0xffffffffu, mine ? (q >> 16) : 0u);
+            if (lane == leader) { fix_w[l] += ((long long)hi << 16) + (long long)lo; cnt_w[l] += __popc(grp); }
             todo &= ~grp;
         }
         __syncwarp();
@@ -203,11 +206,11 @@ __device__ __forceinline__ void irls_solve6(S& c, const long long* ne) {
     for (int i = 0; i < 6; i++)
 #pragma unroll
         for (int j = i; j < 6; j++) {
-            const double vv = scale_pow2((double)ne[kk], -(sx[i] + sx[j]));
+            const double vv = scale_pow2((double)ne[kk], -(sx[i] + sx[j]) - QFRAC_BITS);
             AtA[i * 6 + j] = vv; AtA[j * 6 + i] = vv; kk++;
         }
 #pragma unroll
-    for (int i = 0; i < 6; i++) AtB[i] = scale_pow2((double)ne[21 + i], -(sx[i] + sx[6]));
+    for (int i = 0; i < 6; i++) AtB[i] = scale_pow2((double)ne[21 + i], -(sx[i] + sx[6]) - QFRAC_BITS);
 #pragma unroll
     for (int i = 0; i < 36; i++) { F[i] = AtA[i]; c.AtA[i] = AtA[i]; }
     const int nz = ldlt_factor<6>(F, zero);
@@ -233,7 +236,7 @@ __device__ __forceinline__ bool irls_seg_tail(S& c, const DevParams& prm, long l
     const int N = c.n_valid;
     const long long tot = warp_sum_ll(lf);
     const float aver_res_old = c.aver_res;
-    const int lsh = c.rexp + 9;  // scale of the per-label sums
+    const int lsh = c.rexp + (LABEL_BITS - QSCALE_BITS - 1);  // scale of the per-label sums: |res_c| + |res_d| < 2^(11 - rexp)
     const float aver_new = (float)fixval(tot, lsh) / float(2 * N);  // :666
     if (lane < NC) s_aver_label[lane] = (float)fixval(lf, lsh) / float(2 * (lc + 1));  // :651,667 (counts start at 1)
     __syncwarp();
@@ -275,7 +278,7 @@ __device__ __forceinline__ bool irls_seg_tail(S& c, const DevParams& prm, long l
     }
     int done_i = 0;
     if (lane == 0) {
-        const double rsq = scale_pow2((double)rs_total, -2 * c.rexp);
+        const double rsq = scale_pow2((double)rs_total, -2 * c.rexp - QFRAC_BITS);
         c.res_sq = rsq;
         float delta = 0.f;  // :676
         for (int i = 0; i < 6; i++) { delta = fmaxf(delta, fabsf(c.prev_sol[i] - var[i])); c.prev_sol[i] = var[i]; }
@@ -320,6 +323,8 @@ __device__ __forceinline__ PassItems pass_items(const Arena& a, const LevelGeom&
     const int most = tiles / (4 * PS_WARPS) > 1 ? tiles / (4 * PS_WARPS) : 1;
     if (want > most) want = most;
     if (want < 1) want = 1;
+    const int need = (tiles + MAX_TILES_PER_WARP_ITEM * PS_WARPS - 1) / (MAX_TILES_PER_WARP_ITEM * PS_WARPS);
+    if (want < need) want = need;  // a thread's fixed-point accumulators stay inside their binade (sf_device.cuh)
     p.tiles_per_item = (tiles + want - 1) / want;
     p.items_per_pair = (tiles + p.tiles_per_item - 1) / p.tiles_per_item;
     p.total_items = p.items_per_pair * n;
@@ -368,22 +373,19 @@ irls_pass1_kernel(Arena a, DevParams prm, LevelGeom g, int it, int resident_bloc
         const float inv_c_Cauchy = 1.f / (prm.kc_cauchy * c.aver_res);  // :615
         __syncthreads();
 
-        unsigned acc[27];
+        double acc[27];
 #pragma unroll
-        for (int i = 0; i < 27; i++) acc[i] = 0u;
-        unsigned nrows = 0;
-        for (int i = 0; i < ts.count; i++) {
+        for (int i = 0; i < 27; i++) acc[i] = QMAGIC_D;
+        for (int i = 0; i < ts.count; i++) {  // ts.count <= MAX_TILES_PER_WARP_ITEM (pass_items)
             const unsigned char* tile = ts.wait(i);
             pass1_tile(tile, lane, it, inv_max_c, inv_max_d, inv_c_Cauchy, s_b, s_var, s_mc, s_md, acc);  // per-pair constants stay in shared memory
-            nrows += 4;
             ts.release(i, lane);
         }
-        // remove the nrows copies of the magic constant (mod 2^32), reduce exactly, publish with integer atomics
-        const unsigned corr = nrows * QMAGIC_BITS;
+        // the accumulators' integers, reduced exactly and published with integer atomics
         long long mine = 0;
 #pragma unroll
         for (int i = 0; i < 27; i++) {
-            const long long ws = warp_sum_i32_exact((int)(acc[i] - corr));
+            const long long ws = warp_sum_i64_exact(fixacc_value(acc[i]));
             if (lane == i) mine = ws;
         }
         if (lane < 27) s_part[warp][lane] = mine;
@@ -423,7 +425,7 @@ irls_pass2_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
     int* next_list = (it & 1) ? a.iter_list1 : a.iter_list0;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ int s_fix[PS_WARPS][NC];  // per-warp label sums of round((|res_c|+|res_d|) * 2^(rexp+9)) < 2^20 each
+    __shared__ long long s_fix[PS_WARPS][NC];  // per-warp label sums of round((|res_c|+|res_d|) * 2^(rexp+19)) < 2^30 each
     __shared__ int s_cnt[PS_WARPS][NC];
     __shared__ long long s_rs[PS_WARPS];
     __shared__ float s_var[6];
@@ -456,27 +458,26 @@ irls_pass2_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
         if (tid < 6) s_var[tid] = c.var[tid];
         const float inv_max_c = c.inv_max_c, inv_max_d = c.inv_max_d;
         const int rexp = c.rexp;
-        const float rscale = ldexpf(1.f, rexp), lscale = ldexpf(1.f, rexp + 9);
+        const float rscale = ldexpf(1.f, rexp), lscale = ldexpf(1.f, rexp + (LABEL_BITS - QSCALE_BITS - 1));
         __syncthreads();
         float var[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) var[i] = s_var[i];
 
-        unsigned rs = 0u, nrows = 0u;
+        double rs = QMAGIC_D;
         for (int i = 0; i < ts.count; i++) {
             const unsigned char* tile = ts.wait(i);
             pass2_tile(tile, lane, inv_max_c, inv_max_d, var, rscale, lscale, s_fix[warp], s_cnt[warp], rs);
-            nrows += 4;
             ts.release(i, lane);
         }
-        const long long wrs = warp_sum_i32_exact((int)(rs - nrows * QMAGIC_BITS));
+        const long long wrs = warp_sum_i64_exact(fixacc_value(rs));
         if (lane == 0) s_rs[warp] = wrs;
         __syncthreads();
         if (tid < NC) {
             long long f = 0;
             int n = 0;
 #pragma unroll
-            for (int w = 0; w < PS_WARPS; w++) { f += (long long)s_fix[w][tid]; n += s_cnt[w][tid]; }
+            for (int w = 0; w < PS_WARPS; w++) { f += s_fix[w][tid]; n += s_cnt[w][tid]; }
             if (n) { atomic_add_ll(&c.lab_fix[tid], f); atomicAdd(&c.lab_cnt[tid], n); }
         }
         if (tid == 0) {
@@ -540,7 +541,7 @@ irls_fused_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
     __shared__ float s_mc[7], s_md[7];
     __shared__ long long s_part[W][28];
     __shared__ long long s_ne[27];
-    __shared__ int s_fix[W][NC];
+    __shared__ long long s_fix[W][NC];
     __shared__ int s_cnt[W][NC];
     __shared__ long long s_rs[W];
     __shared__ double s_A[NC * 25];
@@ -579,22 +580,19 @@ irls_fused_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
             if (tid < NC) s_b[tid] = fmaxf(0.f, fminf(1.f, st.b_segm[tid]));  // :624
             const float inv_c_Cauchy = 1.f / (prm.kc_cauchy * st.aver_res);  // :615
             __syncthreads();
-            unsigned acc[27];
+            double acc[27];
 #pragma unroll
-            for (int i = 0; i < 27; i++) acc[i] = 0u;
-            unsigned nrows = 0;
-            for (int i = 0; i < ts.count; i++) {
+            for (int i = 0; i < 27; i++) acc[i] = QMAGIC_D;
+            for (int i = 0; i < ts.count; i++) {  // level_tiles / W <= MAX_TILES_PER_WARP_ITEM (fused_level_ok)
                 const unsigned char* tile = ts.wait(i);
                 pass1_tile(tile, lane, it, inv_max_c, inv_max_d, inv_c_Cauchy, s_b, st.var, s_mc, s_md, acc);
-                nrows += 4;
                 ts.release(i, lane);
             }
             ts.begin(pair_tiles, 0, level_tiles, pattern, warp, lane);  // pass 2's first tiles fly during the reduction and the solve
-            const unsigned corr = nrows * QMAGIC_BITS;
             long long mine = 0;
 #pragma unroll
             for (int i = 0; i < 27; i++) {
-                const long long ws = warp_sum_i32_exact((int)(acc[i] - corr));
+                const long long ws = warp_sum_i64_exact(fixacc_value(acc[i]));
                 if (lane == i) mine = ws;
             }
             if (lane < 27) s_part[warp][lane] = mine;
@@ -614,16 +612,14 @@ irls_fused_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
 #pragma unroll
             for (int i = 0; i < 6; i++) var[i] = st.var[i];
             const int rexp = st.rexp;
-            const float rscale = ldexpf(1.f, rexp), lscale = ldexpf(1.f, rexp + 9);
-            unsigned rs = 0u;
-            nrows = 0u;
+            const float rscale = ldexpf(1.f, rexp), lscale = ldexpf(1.f, rexp + (LABEL_BITS - QSCALE_BITS - 1));
+            double rs = QMAGIC_D;
             for (int i = 0; i < ts.count; i++) {
                 const unsigned char* tile = ts.wait(i);
                 pass2_tile(tile, lane, inv_max_c, inv_max_d, var, rscale, lscale, s_fix[warp], s_cnt[warp], rs);
-                nrows += 4;
                 ts.release(i, lane);
             }
-            const long long wrs = warp_sum_i32_exact((int)(rs - nrows * QMAGIC_BITS));
+            const long long wrs = warp_sum_i64_exact(fixacc_value(rs));
             if (lane == 0) s_rs[warp] = wrs;
             __syncthreads();
             if (warp == 0) {
@@ -631,7 +627,7 @@ irls_fused_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
                 int lc = 0;
                 if (lane < NC)
 #pragma unroll
-                    for (int w = 0; w < W; w++) { lf += (long long)s_fix[w][lane]; lc += s_cnt[w][lane]; }
+                    for (int w = 0; w < W; w++) { lf += s_fix[w][lane]; lc += s_cnt[w][lane]; }
                 long long rs_total = 0;
                 for (int w = 0; w < W; w++) rs_total += s_rs[w];
                 const bool done = irls_seg_tail(st, prm, lf, lc, rs_total, var, it, s_A, s_rhs, s_x, s_zero, s_aver_label, lane,
@@ -796,7 +792,7 @@ static inline int tile_pattern(int cols) {
 }
 // Fused-kernel shapes: many pairs -> small blocks (4 warps, 5 per SM) so that every pair of the batch is resident at once and
 // the serial solves of one pair hide behind the streaming of the others; few pairs -> 12 warps per pair.
-constexpr int FW_SMALL = 4, FB_SMALL = 5;
+constexpr int FW_SMALL = 4, FB_SMALL = 4;
 constexpr size_t fused_dyn_smem(int w) { return (size_t)w * PS_STAGES * TILE_BYTES + (size_t)w * PS_STAGES * sizeof(unsigned long long); }
 void linearise_kernel_attrs();  // sf_k_linearise.cu
 void prepare_kernels() { extern void pass_kernel_attrs_impl(); pass_kernel_attrs_impl(); linearise_kernel_attrs(); }
