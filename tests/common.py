@@ -63,3 +63,27 @@ def oracle_sequence(O, params, depth, inten, history=False, accum=None, want_ima
         if want_images:
             out["b_perpixel"].append(o.b_perpixel()); out["labels"].append(o.labels(0))
     return {k: np.stack(v) for k, v in out.items() if len(v)}
+
+
+def _oracle_job(args):
+    from oracle import oracle as O
+    fields, accum, dc, ic, dp, ip = args
+    o = O.Oracle(O.Params(**fields), accum)
+    T = o.solve_pair(dc, ic, dp, ip)
+    return dict(T=T.copy(), labels=o.labels(0), b_perpixel=o.b_perpixel(), b_segm=o.b_segm(), twist_old=o.twists()[1],
+                irls=o.total_irls(), status=o.status())
+
+
+def oracle_pairs(O, params, jobs, accum=None, workers=None):
+    """Solve independent pairs [(depth_cur, inten_cur, depth_pred, inten_pred), ...] with the oracle on the host cores
+    (twist_odometry_old = 0, as the batched sequence path does); returns one dict of outputs per pair."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    accum = O.ACCUM_EXACT if accum is None else accum
+    fields = {name: getattr(params, name) for name, _ in O.Params._fields_}
+    args = [(fields, accum) + tuple(j) for j in jobs]
+    workers = workers or min(len(args), os.cpu_count() or 1, 32)
+    if workers <= 1:
+        return [_oracle_job(a) for a in args]
+    with ProcessPoolExecutor(workers) as ex:
+        return list(ex.map(_oracle_job, args, chunksize=1))

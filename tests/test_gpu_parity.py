@@ -138,29 +138,30 @@ def test_irls_trace_matches_oracle(gpu, oracle_mod):
     s.close()
 
 
-@pytest.mark.parametrize("scene,n", [("fr1_360", 12), ("dynamic", 8), ("walking_xyz", 8)])
-def test_pose_and_segmentation_parity(gpu, oracle_mod, scene, n):
-    """north_star bar: pose <= 1e-5 m / 1e-5 rad per pair; labels and static mask bit-exact; equal iteration counts."""
+@pytest.mark.parametrize("scene,n,start", [("fr1_360", 40, 10), ("dynamic", 40, 10), ("walking_xyz", 40, 10)])
+def test_pose_and_segmentation_parity(gpu, oracle_mod, scene, n, start):
+    """north_star bar: pose <= 1e-5 m / 1e-5 rad per pair; labels and static mask bit-exact; equal iteration counts.
+    40 pairs per scene at the reference's default 5 levels ("dynamic" from frame 10 holds pair 31, where the first-round
+    integer policy ran two IRLS iterations more than the reference)."""
+    from common import oracle_pairs
     rows, cols = 240, 320
-    d, c = frames(scene, n + 1, rows, cols)
+    d, c = frames(scene, n + 1, rows, cols, start=start)
     p = gpu.default_params(rows, cols)
     s = gpu.StaticFusionSolver(p, max_batch=n)
     r = s.solve_sequence(d, c)
     Tg = r.T_matrices()
+    ref = oracle_pairs(oracle_mod, oracle_params_from(oracle_mod, p), [(d[k + 1], c[k + 1], d[k], c[k]) for k in range(n)])
     worst = (0.0, 0.0)
-    for k in range(n):
-        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k])
-        dt, dr = pose_error(Tg[k], o.T())
+    for k, o in enumerate(ref):
+        dt, dr = pose_error(Tg[k], o["T"])
         worst = (max(worst[0], dt), max(worst[1], dr))
         assert dt <= POSE_TOL_M and dr <= POSE_TOL_RAD, (k, dt, dr)
-        assert r.irls_iters[k] == o.total_irls() and r.status[k] == o.status()
-        assert np.array_equal(r.labels[k].astype(np.int32), o.labels(0))
-        assert np.array_equal(r.b_perpixel[k] > 0.5, o.b_perpixel() > 0.5)
-        assert np.abs(r.b_segm[k] - o.b_segm()).max() < 1e-3
-        assert np.abs(r.twist_old[k] - o.twists()[1]).max() < 1e-5
+        assert r.irls_iters[k] == o["irls"] and r.status[k] == o["status"]
+        assert np.array_equal(r.labels[k].astype(np.int32), o["labels"])
+        assert np.array_equal(r.b_perpixel[k] > 0.5, o["b_perpixel"] > 0.5)
         # bit-identity (see module docstring)
-        assert np.array_equal(Tg[k], o.T()) and np.array_equal(r.b_segm[k], o.b_segm())
-        assert np.array_equal(r.b_perpixel[k], o.b_perpixel()) and np.array_equal(r.twist_old[k], o.twists()[1])
+        assert np.array_equal(Tg[k], o["T"]) and np.array_equal(r.b_segm[k], o["b_segm"])
+        assert np.array_equal(r.b_perpixel[k], o["b_perpixel"]) and np.array_equal(r.twist_old[k], o["twist_old"])
     print(f"{scene}: worst pose error {worst[0]:.2e} m {worst[1]:.2e} rad over {n} pairs")
     s.close()
 
