@@ -94,7 +94,9 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
 void sf_destroy(sf_ctx* ctx);
 
 /* Re-assign the tunables (the drivers rewrite `kb` per frame, StaticFusion-datasets.cpp:156-165).
- * rows, cols, ctf_levels, max_iter_per_level must equal the values given to sf_create. */
+ * rows, cols, ctf_levels, max_iter_per_level must equal the values given to sf_create; everything else, fovh included
+ * (the focal lengths of every level are recomputed), may change.  A call with unchanged values is free: the captured
+ * launch schedule is only rebuilt when a value differs. */
 int sf_set_params(sf_ctx* ctx, const sf_params* p);
 
 /* ---- drop-in trio: one pair at a time, host buffers, the reference's call order ------------------ */

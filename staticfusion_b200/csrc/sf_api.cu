@@ -148,7 +148,30 @@ static int validate(const sf_params* p, int max_batch) {
     }
     if ((long long)(p->rows / 2) * (p->rows / 2) + (long long)(p->cols / 2) * (p->cols / 2) >= 1000000LL)
         return fail(SF_E_INVALID, "resolution exceeds the reference's k-means seed range (KMeans.cpp:91)");
+    // every IRLS pass launch of one solve takes its own dynamic-item counter (Arena::work_ctr)
+    if ((long long)p->ctf_levels * p->max_iter_per_level * (2LL * p->max_iter_irls + 1) > (long long)MAX_WORK_CTRS)
+        return fail(SF_E_INVALID, "ctf_levels * max_iter_per_level * (2 * max_iter_irls + 1) exceeds the per-solve launch counters (4096)");
+    if (!(p->fovh > 0.f) || !(p->fovh < 3.14f)) return fail(SF_E_INVALID, "fovh must be in (0, pi) radians");
     return SF_OK;
+}
+
+// level geometry, constants evaluated exactly as the reference does (FrontEnd.cpp:378-380, 537, 778-780, 874)
+static size_t fill_geometry(sf_ctx* c) {
+    size_t off = 0;
+    const float th = std::tan(0.5f * c->p.fovh);
+    for (int l = 0; l < c->levels; l++) {
+        LevelGeom& g = c->geom[l];
+        g.rows = c->p.rows >> l; g.cols = c->p.cols >> l; g.P = g.rows * g.cols;
+        g.f = float(g.cols) / (2.f * th);
+        g.inv_f = 2.f * th / float(g.cols);
+        g.inv_f_warp = 1.f / g.f;
+        g.disp_u = 0.5f * float(g.cols - 1);
+        g.disp_v = 0.5f * float(g.rows - 1);
+        g.off = off;
+        g.cols_magic = (unsigned)((0x100000000ull + (unsigned long long)g.cols - 1ull) / (unsigned long long)g.cols);
+        off += (size_t)g.P;
+    }
+    return off;
 }
 
 extern "C" {
@@ -193,21 +216,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     if (const char* e = std::getenv("SF_FUSED_MAX_TILES")) c->fused_max_tiles = std::atoi(e);  // tuning / A-B measurements
     c->fused_max_tiles = std::min(c->fused_max_tiles, 4 * MAX_TILES_PER_WARP_ITEM);  // the fused kernel's smallest block has 4 warps
     fill_dev_params(c);
-    // level geometry, constants evaluated exactly as the reference does (FrontEnd.cpp:378-380, 537, 778-780, 874)
-    size_t off = 0;
-    const float th = std::tan(0.5f * p->fovh);
-    for (int l = 0; l < c->levels; l++) {
-        LevelGeom& g = c->geom[l];
-        g.rows = p->rows >> l; g.cols = p->cols >> l; g.P = g.rows * g.cols;
-        g.f = float(g.cols) / (2.f * th);
-        g.inv_f = 2.f * th / float(g.cols);
-        g.inv_f_warp = 1.f / g.f;
-        g.disp_u = 0.5f * float(g.cols - 1);
-        g.disp_v = 0.5f * float(g.rows - 1);
-        g.off = off;
-        g.cols_magic = (unsigned)((0x100000000ull + (unsigned long long)g.cols - 1ull) / (unsigned long long)g.cols);
-        off += (size_t)g.P;
-    }
+    const size_t off = fill_geometry(c);
     Arena& a = c->a;
     a.pyr_stride = off;
     a.P0 = (size_t)c->geom[0].P;
@@ -301,7 +310,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     if (a.dbg) cudaMemsetAsync(a.dbg, 0, sizeof(float) * NPLANES * a.P0 * F, c->stream);
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { sf_destroy(c); return fail(SF_E_CUDA, cudaGetErrorString(e)); }
-    sf::prepare_kernels();
+    sf::prepare_kernels();  // function attributes are per device: set them for this context's device (cudaSetDevice above)
     if (cudaHostAlloc((void**)&c->h_out, sizeof(PairOut) * F, cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc((void**)&c->h_pcar, sizeof(float) * NC * F, cudaHostAllocDefault) != cudaSuccess) { sf_destroy(c); return fail(SF_E_NOMEM, "cudaHostAlloc failed"); }
     *out = c;
@@ -333,11 +342,13 @@ int sf_set_params(sf_ctx* c, const sf_params* p) {
     if (p->rows != c->p.rows || p->cols != c->p.cols || p->ctf_levels != c->p.ctf_levels ||
         p->max_iter_per_level != c->p.max_iter_per_level)
         return fail(SF_E_INVALID, "rows, cols, ctf_levels and max_iter_per_level are fixed at sf_create");
-    if (p->max_iter_irls < 1) return fail(SF_E_INVALID, "max_iter_irls must be >= 1");
-    if (p->enable_segmentation && c->p.ctf_levels < 2) return fail(SF_E_INVALID, "segmentation needs ctf_levels >= 2");
+    if (std::memcmp(p, &c->p, sizeof(sf_params)) == 0) return SF_OK;  // nothing changed: the captured graphs stay valid
+    const int rc = validate(p, c->max_batch);
+    if (rc != SF_OK) return rc;
     c->p = *p;
     fill_dev_params(c);
-    drop_graphs(c);  // kernel arguments are baked into captured graphs
+    fill_geometry(c);  // fovh may have changed: focal lengths of every level
+    drop_graphs(c);    // kernel arguments are baked into captured graphs
     return SF_OK;
 }
 
@@ -917,12 +928,13 @@ int sf_get_outputs(sf_ctx* c, float T_odometry[16], float twist_old_out[6], floa
                    int32_t* labels, int col_major, int* irls_iterations, int* status) {
     if (!c) return fail(SF_E_INVALID, "ctx is NULL");
     if (!c->solved) return fail(SF_E_STATE, "runSolver has not run");
+    if (c->n_pairs != 1) return fail(SF_E_STATE, "sf_get_outputs reads the drop-in path's single pair; use sf_download after a batched solve");
     const int rows = c->p.rows, cols = c->p.cols;
     const size_t n = c->a.P0;
     std::vector<float> bp(b_perpixel ? n : 0);
     std::vector<uint8_t> lb(labels ? n : 0);
-    const int rc = sf_download(c, T_odometry, twist_old_out, b_segm, b_perpixel ? bp.data() : nullptr, labels ? lb.data() : nullptr,
-                               SF_MEM_HOST, irls_iterations, status);
+    const int rc = sf_download_range(c, 0, 1, T_odometry, twist_old_out, b_segm, b_perpixel ? bp.data() : nullptr, labels ? lb.data() : nullptr,
+                                     SF_MEM_HOST, irls_iterations, status, nullptr);
     if (rc) return rc;
     for (int v = 0; v < rows; v++)
         for (int u = 0; u < cols; u++) {

@@ -796,14 +796,11 @@ constexpr int FW_SMALL = 4, FB_SMALL = 4;
 constexpr size_t fused_dyn_smem(int w) { return (size_t)w * PS_STAGES * TILE_BYTES + (size_t)w * PS_STAGES * sizeof(unsigned long long); }
 void linearise_kernel_attrs();  // sf_k_linearise.cu
 void prepare_kernels() { extern void pass_kernel_attrs_impl(); pass_kernel_attrs_impl(); linearise_kernel_attrs(); }
-void pass_kernel_attrs_impl() {
-    static bool done = false;
-    if (done) return;
+void pass_kernel_attrs_impl() {  // per device (function attributes are not shared between devices): called by every sf_create
     cudaFuncSetAttribute(irls_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM);
     cudaFuncSetAttribute(irls_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM);
     cudaFuncSetAttribute(irls_fused_kernel<PS_WARPS, PS_BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem(PS_WARPS));
     cudaFuncSetAttribute(irls_fused_kernel<FW_SMALL, FB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem(FW_SMALL));
-    done = true;
 }
 
 // grid of a pass launch: the resident blocks, or fewer when even the finest partition of every pair has fewer items

@@ -469,12 +469,9 @@ int launch_linearise(const Arena& a, const DevParams& p, const LevelGeom& g, int
     return 1;
 }
 
-void linearise_kernel_attrs() {  // one-time attribute setup, outside stream capture (called by prepare_kernels)
-    static bool done = false;
-    if (done) return;
+void linearise_kernel_attrs() {  // attribute setup for the current device, outside stream capture (called by prepare_kernels in every sf_create)
     cudaFuncSetAttribute(linearise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LIN_MAX_STAGED_SMEM_PER_SM / SF_LIN_BPS));
     cudaFuncSetAttribute(linearise_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 88);  // room for the stages of all resident blocks
-    done = true;
 }
 
 int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c) {

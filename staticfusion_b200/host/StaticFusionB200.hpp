@@ -8,6 +8,7 @@
 // is a minimal column-major float matrix with the same (row, col) indexing and data() layout, so an Eigen user can
 // pass `m.data()` straight through.
 #pragma once
+#include <cstring>
 #include <cstdint>
 #include <cstdio>
 #include <limits>
@@ -195,8 +196,8 @@ private:
         if (!ctx_ || p.ctf_levels != cur_.ctf_levels || p.max_iter_per_level != cur_.max_iter_per_level) {
             sf_destroy(ctx_); ctx_ = nullptr;
             check(sf_create(&ctx_, &p, device_, 1, 0));
-        } else {
-            check(sf_set_params(ctx_, &p));
+        } else if (std::memcmp(&p, &cur_, sizeof(sf_params)) != 0) {
+            check(sf_set_params(ctx_, &p));  // only when a field changed (kb per frame, StaticFusion-datasets.cpp:156-165)
         }
         cur_ = p;
     }

@@ -233,8 +233,14 @@ class StaticFusionSolver:
         check(self.L.sf_set_history(self.h, int(bool(on))))
 
     def solve_sequence(self, depth, inten, twist_old=None, want_images=True, history=False, halo=0, out=None) -> BatchResult:
-        """n frames -> n-1 pairs.  history: run the 5-frame residual stage (pairs 0..3 of the call have none);
-        halo: leading pairs that are solved only to provide that history and are dropped from the result."""
+        """n frames -> n-1 pairs, all solved concurrently.  history: run the 5-frame residual stage (pairs 0..3 of the call
+        have none); halo: leading pairs that are solved only to provide that history and are dropped from the result.
+
+        Cross-frame state: the reference chains twist_odometry_old from one frame to the next (FrontEnd.cpp:1143-1144 ->
+        :733-751, read only by the motion filter).  Pairs of a batch are independent, so every pair starts from
+        `twist_old` (default 0: SURVEY section 8e's frame-sharded choice) -- with use_motion_filter = 1 the increments are
+        therefore filtered towards zero velocity and differ from a sequential run of the reference over the same frames.
+        `solve_sequence_chained` reproduces the sequential semantics."""
         nf = int(depth.shape[0])
         a = [_addr(x) for x in (depth, inten)]
         if a[0][1] != a[1][1]:
@@ -248,6 +254,21 @@ class StaticFusionSolver:
         self._n = nf - 1
         check(self.L.sf_launch(self.h))
         self.download_range(halo, n, r)
+        return r
+
+    def solve_sequence_chained(self, depth, inten, twist_old=None, want_images=True) -> BatchResult:
+        """The reference's own frame-to-frame order (StaticFusion-datasets.cpp:109-144): pair k is solved after pair k-1 and
+        receives its twist_odometry_old (FrontEnd.cpp:1143-1144).  One pair per launch: for parity runs, not throughput."""
+        n = int(depth.shape[0]) - 1
+        r = BatchResult(n, self.rows, self.cols, want_images)
+        tw = np.zeros((1, 6), np.float32) if twist_old is None else np.ascontiguousarray(twist_old, np.float32).reshape(1, 6)
+        for k in range(n):
+            one = self.solve_batch(depth[k + 1:k + 2], inten[k + 1:k + 2], depth[k:k + 1], inten[k:k + 1], twist_old=tw, want_images=want_images)
+            for name in ("T", "twist_old", "b_segm", "irls_iters", "status"):
+                getattr(r, name)[k] = getattr(one, name)[0]
+            if want_images:
+                r.b_perpixel[k] = one.b_perpixel[0]; r.labels[k] = one.labels[0]
+            tw = one.twist_old[0:1].copy()
         return r
 
     def download_range(self, first: int, n: int, r: BatchResult, at: int = 0):

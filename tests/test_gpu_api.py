@@ -247,3 +247,47 @@ def test_stress_resolution_1280x960_smoke(gpu, oracle_mod):
     assert np.array_equal(r.b_perpixel[0] > 0.5, o.b_perpixel() > 0.5)
     assert r.irls_iters[0] == o.total_irls()
     s.close()
+
+
+def test_contexts_on_two_devices_in_one_process(gpu):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a second context on another GPU of the same
+    process must solve, and give the same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d, c = frames("dynamic", 3, 240, 320)
+    p = gpu.default_params(240, 320)
+    a = gpu.StaticFusionSolver(p, device=0, max_batch=2)
+    b = gpu.StaticFusionSolver(p, device=1, max_batch=2)
+    ra, rb = a.solve_sequence(d, c), b.solve_sequence(d, c)
+    assert same(ra, rb)
+    a.close(); b.close()
+
+
+def test_get_outputs_is_the_single_pair_call(gpu):
+    """sf_get_outputs copies one pair into one-pair buffers: after a batched solve it must refuse instead of overflowing."""
+    d, c = frames("dynamic", 4, 240, 320)
+    s = gpu.StaticFusionSolver(gpu.default_params(240, 320), max_batch=3)
+    s.solve_sequence(d, c)
+    with pytest.raises(gpu.SfError) as e:
+        s.buildSegmImage()
+    assert e.value.code == -4
+    s.close()
+
+
+def test_changed_fovh_takes_effect(gpu, oracle_mod):
+    """sf_set_params recomputes the per-level focal lengths when fovh changes (and is a no-op when nothing changes)."""
+    from common import oracle_params_from
+    d, c = frames("dynamic", 2, 240, 320)
+    p = gpu.default_params(240, 320)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r1 = s.solve_sequence(d, c)
+    s.set_params(p)  # unchanged
+    assert same(r1, s.solve_sequence(d, c))
+    p2 = gpu.default_params(240, 320, fovh=float(np.float32(np.pi * 58.0 / 180.0)))
+    s.set_params(p2)
+    r2 = s.solve_sequence(d, c)
+    o = oracle_mod.Oracle(oracle_params_from(oracle_mod, p2), oracle_mod.ACCUM_EXACT)
+    o.solve_pair(d[1], c[1], d[0], c[0])
+    assert not np.array_equal(r1.T, r2.T) and np.array_equal(r2.T_matrices()[0], o.T())
+    s.close()

@@ -237,6 +237,24 @@ def test_motion_filter_state_is_threaded_through(gpu, oracle_mod):
     s.close()
 
 
+def test_chained_sequence_reproduces_the_sequential_reference_order(gpu, oracle_mod):
+    """solve_sequence_chained: pair k receives pair k-1's twist_odometry_old, as a sequential run of the reference does."""
+    rows, cols, n = 240, 320, 5
+    d, c = frames("walking_xyz", n + 1, rows, cols)
+    p = gpu.default_params(rows, cols)
+    s = gpu.StaticFusionSolver(p, max_batch=1)
+    r = s.solve_sequence_chained(d, c)
+    tw = None
+    for k in range(n):
+        o = run_oracle(oracle_mod, p, d[k + 1], c[k + 1], d[k], c[k], twist_old=tw)
+        tw = o.twists()[1]
+        assert np.array_equal(r.T_matrices()[k], o.T()) and np.array_equal(r.twist_old[k], tw), k
+        assert np.array_equal(r.b_perpixel[k], o.b_perpixel()) and r.irls_iters[k] == o.total_irls()
+    batch = gpu.StaticFusionSolver(p, max_batch=n).solve_sequence(d, c)
+    assert np.array_equal(batch.T[0], r.T[0]) and not np.array_equal(batch.T[1:], r.T[1:])  # the chain matters from pair 1 on
+    s.close()
+
+
 def test_degenerate_inputs(gpu):
     """empty / identical inputs return identity and a status bit instead of the reference's NaN."""
     rows, cols = 240, 320
