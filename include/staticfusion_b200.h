@@ -245,6 +245,19 @@ int sf_profile_read_records(sf_ctx* ctx, int capacity, int* cls, int* level, flo
 /* Per pair and step (ctf_levels*max_iter_per_level steps, index level*max_iter_per_level + k) of the last solve:
  * valid pixels N (0 = step not executed) and IRLS iterations run.  Arrays hold n_pairs*steps ints. */
 int sf_get_step_stats(sf_ctx* ctx, int* n_valid, int* irls_iters);
+/* Lloyd iterations kMeans3DCoord ran for every pair of the last solve (1..9, KMeans.cpp:167-228; 0 without segmentation). */
+int sf_get_kmeans_iterations(sf_ctx* ctx, int* iterations);
+/* on != 0: the host->device copies of sf_upload_sequence_raw (host input) and the device->host copies of
+ * sf_download_range_begin run on two extra streams of the context, ordered against the solve stream by events: a
+ * context's next upload overlaps its current solve, its download overlaps the solves of other contexts, and no call
+ * waits on the host (sf_download_range_end does).  Results are unchanged.  Replaces the blocking glDownload / upload
+ * round trips around the solver in the drivers (StaticFusion-datasets.cpp:166-190). */
+int sf_set_copy_streams(sf_ctx* ctx, int on);
+/* The result rows of the last solve where they lie in DEVICE memory: n_rows rows of row_floats 4-byte words each --
+ * T_odometry (16, row-major), twist_odometry_old (6), b_segm (24), then two int32 (IRLS iterations, status bits).  Valid
+ * until the next upload / launch on this context; ordered after the solve on sf_stream(ctx).  For collectives that gather
+ * the per-frame poses across GPUs without a host round trip (StaticFusion-datasets.cpp:186-196 reads them per frame). */
+int sf_result_rows_device(sf_ctx* ctx, const float** rows, int* n_rows, int* row_floats);
 
 /* ---- introspection for parity tests ------------------------------------------------------------ */
 /* Halt the next solves right after the linearisation of step (level*max_iter_per_level + k); -1 = run to the end. */

@@ -13,7 +13,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "libsf_oracle.so")
+# ORC_VARIANT=native loads the -O3 -march=native build of the same source (make native; CPU baseline only)
+_VARIANT = os.environ.get("ORC_VARIANT", "")
+_LIB_PATH = os.path.join(_HERE, "_build", "libsf_oracle_native.so" if _VARIANT == "native" else "libsf_oracle.so")
 
 NUM_CLUSTERS = 24
 TRACE_MAX_IRLS = 12
@@ -23,6 +25,7 @@ TRACE_STEP = TRACE_HDR + TRACE_MAX_IRLS * TRACE_IRLS
 ACCUM_F32 = 0
 ACCUM_EXACT = 1
 ACCUM_F64 = 2
+STAGES = ("pyramid", "kmeans", "warp", "linearise", "irls", "seg_solve", "pose_update", "segm_image")
 
 
 class Params(C.Structure):
@@ -40,7 +43,7 @@ def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, "sf_oracle.cpp"), os.path.join(_HERE, "sf_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["native"] if _VARIANT == "native" else []))
     return _LIB_PATH
 
 
@@ -64,6 +67,7 @@ def lib():
         L.orc_create_image_pyramid.argtypes = [C.c_void_p, C.c_int]
         L.orc_run_solver.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_build_segm_image.argtypes = [C.c_void_p]
+        L.orc_get_stage_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         L.orc_kmeans.argtypes = [C.c_void_p]
         L.orc_filter_depth.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_float, C.c_int, fp]
         L.orc_convert_frame.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, fp, fp,
@@ -213,6 +217,12 @@ class Oracle:
 
     def kmeans(self):
         self.L.orc_kmeans(self.h)
+
+    def stage_seconds(self, reset=True) -> dict:
+        """Wall time per stage (std::chrono::steady_clock inside the oracle) since creation / the last reset."""
+        out = (C.c_double * len(STAGES))()
+        self.L.orc_get_stage_seconds(self.h, out, int(reset))
+        return dict(zip(STAGES, [float(x) for x in out]))
 
     # ---- 5-frame history (FrontEnd.cpp:896-1069 and the drivers' ring buffers) ----
     def buffer_set(self, slot, depth, inten, T=None):

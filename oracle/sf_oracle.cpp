@@ -24,6 +24,7 @@
 #include "sf_oracle.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -80,6 +81,17 @@ inline int scale_exponent(float bound) {
     return s;
 }
 inline int64_t qprod(float a, float b) { return (int64_t)std::nearbyint(std::ldexp((double)a * (double)b, ORC_QFRAC_BITS)); }
+
+struct StageTimer { /* adds the scope's wall time to one stage cell (nested scopes subtract themselves from the outer one) */
+    double* cell; double* outer;
+    std::chrono::steady_clock::time_point t0;
+    StageTimer(double* c, double* o = nullptr) : cell(c), outer(o), t0(std::chrono::steady_clock::now()) {}
+    ~StageTimer() {
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *cell += dt;
+        if (outer) *outer -= dt;
+    }
+};
 
 /* =====================================================================================
  * Small dense algebra (templated on float / double)
@@ -343,6 +355,9 @@ struct orc_ctx {
 
     float max_wc_raw, max_wd_raw;
     int status, total_irls;
+    /* per-stage wall time (std::chrono::steady_clock): pyramid, k-means, warp, linearise, IRLS,
+     * seg-solve, pose update, per-pixel image */
+    double stage_s[ORC_NUM_STAGES] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<float> trace;
     float* cur_trace;
 
@@ -413,6 +428,7 @@ void orc_ctx::init(const orc_params& pp, int accum_mode) {
 
 /* FrontEnd.cpp:256-391 */
 void orc_ctx::createImagePyramid(bool old_im) {
+    StageTimer tm(&stage_s[0]);
     const float max_depth_dif = 0.1f;
     for (int i = 0; i < pyr_levels; i++) {
         const int ci = cols >> i, ri = rows >> i;
@@ -1245,7 +1261,7 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         }
         for (int l = 0; l < NC; l++) aver_res_label[l] /= float(2 * num_pix_label[l]);
 
-        if (p.enable_segmentation) solveSegmIteration(aver_res_label, aver_res_old, lap); /* :672 */
+        if (p.enable_segmentation) { StageTimer tm(&stage_s[5], &stage_s[4]); solveSegmIteration(aver_res_label, aver_res_old, lap); } /* :672 */
 
         float delta_sol_max = 0.f; /* :676 */
         for (int i = 0; i < 6; i++) delta_sol_max = std::max(delta_sol_max, std::fabs(prev_sol[i] - Var[i]));
@@ -1279,7 +1295,7 @@ void orc_ctx::solveOdometryAndSegmJoint() {
         general_inverse<float>(6, F, inv);
         for (int i = 0; i < 36; i++) est_cov[i] = (double)(inv[i] * (float)res_sq);
     }
-    filterEstimateAndComputeT(Var);
+    { StageTimer tm(&stage_s[6], &stage_s[4]); filterEstimateAndComputeT(Var); }
 }
 
 /* FrontEnd.cpp:713-772 */
@@ -1382,6 +1398,7 @@ void orc_ctx::runSolver(bool create_image_pyr, int stop_step) {
     std::fill(trace.begin(), trace.end(), 0.f);
     if (create_image_pyr) createImagePyramid(false);
     if (p.enable_segmentation) {
+        StageTimer tm(&stage_s[1]);
         kMeans3DCoord();
         createClustersPyramidUsingKMeans();
     } else {
@@ -1404,15 +1421,23 @@ void orc_ctx::runSolver(bool create_image_pyr, int stop_step) {
                 intensityWarpedPyr[image_level] = intensityPredPyr[image_level];
                 xxWarpedPyr[image_level] = xxPredPyr[image_level];
                 yyWarpedPyr[image_level] = yyPredPyr[image_level];
-            } else
+            } else {
+                StageTimer tm(&stage_s[2]);
                 warpImagesAccurateInverse();
-            calculateCoord();
-            calculateDerivatives();
-            computeWeights();
-            computeSegPrior();
+            }
+            {
+                StageTimer tm(&stage_s[3]);
+                calculateCoord();
+                calculateDerivatives();
+                computeWeights();
+                computeSegPrior();
+            }
             for (int l = 0; l < NC; l++) { cur_trace[8 + l] = b_prior[l]; cur_trace[32 + l] = lambda_t_w[l]; }
             if (step == stop_step) return;
-            solveOdometryAndSegmJoint();
+            {
+                StageTimer tm(&stage_s[4]);
+                solveOdometryAndSegmJoint();
+            }
             for (int q = 0; q < 6; q++) { cur_trace[56 + q] = twist_level_odometry[q]; cur_trace[79 + q] = twist_odometry[q]; }
             for (int q = 0; q < 16; q++) cur_trace[62 + q] = T_odometry[q];
             cur_trace[78] = (float)status;
@@ -1449,6 +1474,7 @@ void orc_ctx::runSolver(bool create_image_pyr, int stop_step) {
 
 /* SegmentationBackground.cpp:176-197 */
 void orc_ctx::buildSegmImage() {
+    StageTimer tm(&stage_s[7]);
     const ImgI& labels_maxres = clusterAllocation[0];
     for (int u = 0; u < cols; u++)
         for (int v = 0; v < rows; v++) {
@@ -1807,6 +1833,9 @@ void orc_quat_from_rotation(const float T[16], float q[4]) {
     }
 }
 int orc_get_status(const orc_ctx* c) { return c->status; }
+void orc_get_stage_seconds(orc_ctx* c, double out[ORC_NUM_STAGES], int reset) {
+    for (int i = 0; i < ORC_NUM_STAGES; i++) { out[i] = c->stage_s[i]; if (reset) c->stage_s[i] = 0; }
+}
 int orc_get_total_irls(const orc_ctx* c) { return c->total_irls; }
 
 int orc_get_image(const orc_ctx* c, const char* name, int L, float* out) {

@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define ORC_NUM_CLUSTERS 24
+#define ORC_NUM_STAGES 8 /* pyramid, k-means, warp, linearise, IRLS, seg-solve, pose update, per-pixel image */
 #define ORC_TRACE_MAX_IRLS 12
 #define ORC_TRACE_HDR 96
 #define ORC_TRACE_IRLS 34
@@ -72,6 +73,8 @@ void orc_create_image_pyramid(orc_ctx* c, int old_im);
 /* stop_step >= 0: return right after computeSegPrior of step (level*max_iter_per_level + k) for stage dumps */
 void orc_run_solver(orc_ctx* c, int create_image_pyr, int stop_step);
 void orc_build_segm_image(orc_ctx* c);
+/* wall time accumulated per stage since creation / the last reset (std::chrono::steady_clock; CPU baseline) */
+void orc_get_stage_seconds(orc_ctx* c, double out[ORC_NUM_STAGES], int reset);
 
 /* 5-frame history (StaticFusion.h:92-99; FrontEnd.cpp:896-1069).  The drivers copy the current frame and T_odometry
  * into slot im_count % 5 after every frame (StaticFusion-datasets.cpp:114-116, 130-132, 182-184) and call

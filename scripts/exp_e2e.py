@@ -18,18 +18,18 @@ from staticfusion_b200.solver import BatchResult
 def main():
     F = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     config = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-    name, rows, cols, levels, _, scene = bench.CONFIGS[config]
-    d, c = bench.make_frames(scene, 65, rows, cols)
+    name, rows, cols, levels, _, scene, _ = bench.CONFIGS[config]
+    bgr, mm = bench.make_raw_frames(scene, 65, rows, cols)
     seq = bench.sequence_indices(F + 1, 65)
-    hd = torch.from_numpy(np.ascontiguousarray(d[seq])).pin_memory()
-    hc = torch.from_numpy(np.ascontiguousarray(c[seq])).pin_memory()
+    hd = torch.from_numpy(np.ascontiguousarray(bgr[seq])).pin_memory()           # colour, 3 B / px
+    hc = torch.from_numpy(np.ascontiguousarray(mm[seq].view(np.int16))).pin_memory()  # depth mm, 2 B / px
     gd, gc = torch.empty_like(hd, device="cuda"), torch.empty_like(hc, device="cuda")
     w = torch.empty((F, rows, cols), dtype=torch.float32, device="cuda")
     l = torch.empty((F, rows, cols), dtype=torch.uint8, device="cuda")
     hw = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
     hl = torch.empty(l.shape, dtype=l.dtype, pin_memory=True)
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    in_b = hd.numel() * 4 + hc.numel() * 4
+    in_b = hd.numel() + hc.numel() * 2
     out_b = w.numel() * 4 + l.numel()
 
     def h2d():
@@ -54,12 +54,16 @@ def main():
     del gd, gc, w, l
     torch.cuda.empty_cache()
     p = sf.default_params(rows, cols, ctf_levels=levels)
-    for chunk, n_ctx, images in ((128, 3, True), (128, 3, False), (128, 4, True), (256, 2, True), (256, 3, True), (64, 6, True), (171, 3, True)):
-        ps = sf.PipelinedSolver(p, chunk=chunk, n_ctx=n_ctx)
-        outs = [BatchResult(F, rows, cols, images, pinned=True) for _ in range(2)]
+    shapes = [tuple(int(v) for v in x.split("x")) for x in os.environ.get("SHAPES", "256x3,256x4,512x2,512x3,171x4,128x6").split(",")]
+    np_bgr, np_mm = hd.numpy(), hc.numpy().view(np.uint16)
+    for chunk, n_ctx, cs in [(a, b, True) for a, b in shapes] + [(shapes[0][0], shapes[0][1], False)]:
+        images = True
+        ps = sf.PipelinedSolver(p, chunk=chunk, n_ctx=n_ctx, copy_streams=cs)
+        depth = int(os.environ.get("DEPTH", "2"))  # steps in flight behind the one being enqueued
+        outs = [BatchResult(F, rows, cols, images, pinned=True) for _ in range(depth + 1)]
 
         def step(k):
-            return ps.solve_sequence(hd.numpy(), hc.numpy(), out=outs[k % 2], want_images=images, wait=False)
+            return ps.solve_sequence_raw(np_bgr, np_mm, 1, out=outs[k % (depth + 1)], want_images=images, wait=False)
 
         for k in range(2):
             step(k)
@@ -67,16 +71,15 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         K = 10
-        prev = None
+        inflight = []
         for k in range(K):
-            cur = step(k)
-            if prev is not None:
-                ps.wait_for(prev)
-            prev = cur
+            inflight.append(step(k))
+            if len(inflight) > depth:
+                ps.wait_for(inflight.pop(0))
         ps.flush()
         torch.cuda.synchronize()
         ms = 1e3 * (time.perf_counter() - t0) / K
-        print(f"e2e: chunk {chunk} x {n_ctx} ctx, images={images}: {ms:.3f} ms/step  {F / ms * 1e3:.0f} frames/s", flush=True)
+        print(f"e2e: chunk {chunk} x {n_ctx} ctx, copy streams={cs}, depth {depth}: {ms:.3f} ms/step  {F / ms * 1e3:.0f} frames/s", flush=True)
         ps.close()
 
 

@@ -16,13 +16,13 @@ import staticfusion_b200 as sf
 def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     config = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-    name, rows, cols, levels, F, scene = bench.CONFIGS[config]
-    d, c = bench.make_frames(scene, 17, rows, cols)
+    name, rows, cols, levels, F, scene, _ = bench.CONFIGS[config]
+    bgr, mm = bench.make_raw_frames(scene, 17, rows, cols)
     seq = bench.sequence_indices(batch + 1, 17)
-    g = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (d[seq], c[seq])]
+    g = [torch.from_numpy(np.ascontiguousarray(bgr[seq])).cuda(), torch.from_numpy(np.ascontiguousarray(mm[seq].view(np.int16))).cuda()]
     s = sf.StaticFusionSolver(sf.default_params(rows, cols, ctf_levels=levels), max_batch=batch)
     for _ in range(2):
-        s.upload_sequence(*g)
+        s.upload_sequence_raw(g[0], g[1], 1)
         s.launch()
         s.sync()
     print("launches per solve:", s.last_launch_count)

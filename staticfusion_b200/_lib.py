@@ -33,6 +33,7 @@ EXPORTS = [
     "sf_buffer_set", "sf_buffer_push", "sf_compute_residuals_against_previous_image",
     "sf_get_per_cluster_average_residual", "sf_set_history", "sf_download_range", "sf_filter_depth",
     "sf_convert_frames", "sf_upload_sequence_raw", "sf_last_lane_count", "sf_download_range_begin", "sf_download_range_end",
+    "sf_get_kmeans_iterations", "sf_result_rows_device", "sf_set_copy_streams",
 ]
 PROF_CLASSES = 9
 PROF_LEVELS = 8
@@ -127,6 +128,9 @@ def lib():
     L.sf_profile_read.argtypes = [vp, fp, ip]
     L.sf_profile_read_records.argtypes = [vp, C.c_int, ip, ip, fp, ip]
     L.sf_get_step_stats.argtypes = [vp, ip, ip]
+    L.sf_get_kmeans_iterations.argtypes = [vp, ip]
+    L.sf_set_copy_streams.argtypes = [vp, C.c_int]
+    L.sf_result_rows_device.argtypes = [vp, C.POINTER(C.c_void_p), ip, ip]
     L.sf_last_error.restype = C.c_char_p
     L.sf_abi_version.restype = C.c_int
     _lib = L

@@ -5,6 +5,7 @@
 // without any host synchronisation.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,6 +82,13 @@ struct sf_ctx {
     // image-sequence loader scratch (grown on demand): raw inputs and converted outputs of sf_convert_frames
     uint8_t* d_cvt = nullptr;
     size_t cvt_cap = 0;
+    // copy streams (sf_set_copy_streams): host->device copies of raw frames and device->host copies of results run on their own
+    // streams, ordered against the solve stream by events, so that a context's transfers overlap the solves of other contexts
+    // (and its own next upload overlaps its current solve) without any host-side wait
+    bool copy_streams = false;
+    cudaStream_t ul_stream = nullptr, dl_stream = nullptr;
+    cudaEvent_t ev_ul = nullptr, ev_cvt = nullptr, ev_solved = nullptr, ev_dl = nullptr;
+    bool cvt_recorded = false, dl_recorded = false;
 };
 
 static void drop_graphs(sf_ctx* c) {
@@ -333,6 +341,9 @@ void sf_destroy(sf_ctx* c) {
     for (int l = 1; l < sf_ctx::MAX_LANES; l++) { if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ul_stream) cudaStreamDestroy(c->ul_stream);
+    if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
+    for (cudaEvent_t e : {c->ev_ul, c->ev_cvt, c->ev_solved, c->ev_dl}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -546,10 +557,30 @@ int sf_launch(sf_ctx* c) {
     if (!c->uploaded) return fail(SF_E_STATE, "no batch uploaded");
     CU(cudaSetDevice(c->device));
     // batched solves carry no history between calls: perClusterAverageResidual starts as NaN (FrontEnd.cpp:105)
+    if (c->copy_streams && c->dl_recorded) CU(cudaStreamWaitEvent(c->stream, c->ev_dl, 0));  // the last results have left the arena
     CU(cudaMemsetAsync(c->a.pcar, 0xff, sizeof(float) * NC * c->n_pairs, c->stream));
     const int rc = launch_solve(c, true);
-    if (rc == SF_OK) c->solved = true;
+    if (rc == SF_OK) {
+        c->solved = true;
+        if (c->copy_streams) CU(cudaEventRecord(c->ev_solved, c->stream));
+    }
     return rc;
+}
+
+int sf_set_copy_streams(sf_ctx* c, int on) {
+    if (!c) return fail(SF_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (on && !c->ul_stream) {
+        CU(cudaStreamCreateWithFlags(&c->ul_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&c->ev_ul, &c->ev_cvt, &c->ev_solved, &c->ev_dl}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    if (c->dl_stream) CU(cudaStreamSynchronize(c->dl_stream));
+    if (c->ul_stream) CU(cudaStreamSynchronize(c->ul_stream));
+    c->copy_streams = on != 0;
+    c->cvt_recorded = c->dl_recorded = false;
+    return SF_OK;
 }
 
 int sf_set_history(sf_ctx* c, int on) {
@@ -588,11 +619,17 @@ int sf_download_range_begin(sf_ctx* c, int first_pair, int n, float* T_odometry,
     if (n == 0) return SF_OK;
     CU(cudaSetDevice(c->device));
     const Arena& a = c->a;
-    CU(cudaMemcpyAsync(c->h_out, a.out + first_pair, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    cudaStream_t st = c->stream;
+    if (c->copy_streams) {  // the copies run on the download stream, behind the solve
+        CU(cudaStreamWaitEvent(c->dl_stream, c->ev_solved, 0));
+        st = c->dl_stream;
+    }
+    CU(cudaMemcpyAsync(c->h_out, a.out + first_pair, sizeof(PairOut) * n, cudaMemcpyDeviceToHost, st));
     const cudaMemcpyKind kind = (out_space == SF_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, a.b_perpixel + (size_t)first_pair * a.P0, sizeof(float) * a.P0 * n, kind, c->stream));
-    if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, a.P0, a.labels + (size_t)first_pair * a.pyr_stride, a.pyr_stride, a.P0, (size_t)n, kind, c->stream));
-    if (per_cluster_residual) CU(cudaMemcpyAsync(c->h_pcar, a.pcar + (size_t)first_pair * NC, sizeof(float) * NC * n, cudaMemcpyDeviceToHost, c->stream));
+    if (b_perpixel) CU(cudaMemcpyAsync(b_perpixel, a.b_perpixel + (size_t)first_pair * a.P0, sizeof(float) * a.P0 * n, kind, st));
+    if (labels_u8) CU(cudaMemcpy2DAsync(labels_u8, a.P0, a.labels + (size_t)first_pair * a.pyr_stride, a.pyr_stride, a.P0, (size_t)n, kind, st));
+    if (per_cluster_residual) CU(cudaMemcpyAsync(c->h_pcar, a.pcar + (size_t)first_pair * NC, sizeof(float) * NC * n, cudaMemcpyDeviceToHost, st));
+    if (c->copy_streams) { CU(cudaEventRecord(c->ev_dl, c->dl_stream)); c->dl_recorded = true; }
     return SF_OK;
 }
 
@@ -601,7 +638,8 @@ int sf_download_range_end(sf_ctx* c) {
     if (!c->dl.on) return fail(SF_E_STATE, "no download in flight");
     const sf_ctx::PendingDownload d = c->dl;
     c->dl.on = false;
-    CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_streams && d.n) CU(cudaStreamSynchronize(c->dl_stream));
+    else CU(cudaStreamSynchronize(c->stream));
     if (d.pcar && d.n) std::memcpy(d.pcar, c->h_pcar, sizeof(float) * NC * d.n);
     for (int k = 0; k < d.n; k++) {
         const PairOut& o = c->h_out[k];
@@ -875,13 +913,20 @@ int sf_upload_sequence_raw(sf_ctx* c, int n_frames, const uint8_t* bgr, const ui
         const size_t o_raw = align256(3 * Pf * n);
         const int rc = cvt_reserve(c, o_raw + align256(2 * Pf * n));
         if (rc) return rc;
-        CU(cudaMemcpyAsync(c->d_cvt, bgr, 3 * Pf * n, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->d_cvt + o_raw, depth_raw, 2 * Pf * n, cudaMemcpyHostToDevice, c->stream));
+        cudaStream_t st = c->stream;
+        if (c->copy_streams) {  // the frames travel on the upload stream while this context (and the others) solve
+            st = c->ul_stream;
+            if (c->cvt_recorded) CU(cudaStreamWaitEvent(st, c->ev_cvt, 0));  // the last conversion has read the scratch
+        }
+        CU(cudaMemcpyAsync(c->d_cvt, bgr, 3 * Pf * n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_cvt + o_raw, depth_raw, 2 * Pf * n, cudaMemcpyHostToDevice, st));
+        if (c->copy_streams) { CU(cudaEventRecord(c->ev_ul, st)); CU(cudaStreamWaitEvent(c->stream, c->ev_ul, 0)); }
         s_bgr = c->d_cvt; s_raw = (const uint16_t*)(c->d_cvt + o_raw);
     }
     // frame k converts straight into the level-0 slot of its pyramids (prediction := previous raw frame)
     launch_convert_frames(s_bgr, s_raw, c->p.rows, c->p.cols, res_factor, n_frames, c->a.pyr_i, c->a.pyr_d, c->a.pyr_stride, nullptr, nullptr, c->stream);
     CU(cudaGetLastError());
+    if (c->copy_streams && in_space != SF_MEM_DEVICE) { CU(cudaEventRecord(c->ev_cvt, c->stream)); c->cvt_recorded = true; }
     const int n_pairs = n_frames - 1;
     std::vector<int>&ci = c->h_ci, &pi = c->h_pi;
     if ((int)ci.size() != n_pairs || ci[0] != 1 || pi[0] != 0) {
@@ -991,6 +1036,27 @@ int sf_get_step_stats(sf_ctx* c, int* n_valid, int* irls_iters) {
     std::vector<int> h(2 * n);
     CU(cudaMemcpy(h.data(), c->a.stepstat, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; i++) { n_valid[i] = h[2 * i]; irls_iters[i] = h[2 * i + 1]; }
+    return SF_OK;
+}
+
+int sf_get_kmeans_iterations(sf_ctx* c, int* iterations) {
+    if (!c || !iterations) return fail(SF_E_INVALID, "NULL argument");
+    if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!c->p.enable_segmentation) { for (int k = 0; k < c->n_pairs; k++) iterations[k] = 0; return SF_OK; }
+    CU(cudaMemcpy2D(iterations, sizeof(int), reinterpret_cast<const char*>(c->a.ctl) + offsetof(PairCtl, km_iters), sizeof(PairCtl), sizeof(int),
+                    (size_t)c->n_pairs, cudaMemcpyDeviceToHost));
+    return SF_OK;
+}
+
+int sf_result_rows_device(sf_ctx* c, const float** rows, int* n_rows, int* row_floats) {
+    if (!c || !rows || !n_rows || !row_floats) return fail(SF_E_INVALID, "NULL argument");
+    if (!c->solved) return fail(SF_E_STATE, "nothing has been solved");
+    static_assert(sizeof(PairOut) == 48 * sizeof(float), "result row layout");
+    *rows = reinterpret_cast<const float*>(c->a.out);
+    *n_rows = c->n_pairs;
+    *row_floats = (int)(sizeof(PairOut) / sizeof(float));
     return SF_OK;
 }
 

@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(KM_THREADS, SF_KM_BPS) kmeans_kernel(Arena a, 
     __shared__ float4 s_queue[KM_WARPS][KM_QUEUE];  // per-warp queue of pixels waiting for the candidate loop: (z, x, y, pixel << 5 | label)
 #endif
     __shared__ int s_dl[NC][10];  // limb sums of the incremental update: 3 coordinates x 3 limbs + count
+    int its_done = 0;
     for (int it = 0; it < 9; it++) {
+        its_done = it + 1;
         build_cand_table_block(cen, L.t, scratch, tid, KM_THREADS);
         if (tid == 0) s_list_n = 0;
         for (int i = tid; i < NC * 10; i += KM_THREADS) (&s_dl[0][0])[i] = 0;
@@ -446,6 +448,7 @@ __global__ void __launch_bounds__(KM_THREADS, SF_KM_BPS) kmeans_kernel(Arena a, 
     // publish centres + the final sorted table for the full-resolution labelling (KMeans.cpp:232-259)
     build_cand_table_block(cen, L.t, scratch, tid, KM_THREADS);
     if (tid < NC) { c.kmeans[tid] = cen[tid].x; c.kmeans[NC + tid] = cen[tid].y; c.kmeans[2 * NC + tid] = cen[tid].z; }
+    if (tid == 0) c.km_iters = its_done;
     for (int i = tid; i < NC * NC; i += KM_THREADS) { c.tbl_dist[i] = L.t.cand[i / NC][i % NC].w; c.tbl_idx[i] = (&L.t.tidx[0][0])[i]; }
 }
 

@@ -72,6 +72,82 @@ def gather_rows(local_rows: np.ndarray, n_pairs: int, device=None) -> np.ndarray
     return table
 
 
+def rows_from_device_layout(rows: np.ndarray) -> np.ndarray:
+    """Device result rows (sf_result_rows_device: T row-major, counters as int32 bit patterns) -> the host row layout of
+    pack_rows (T column-major like Eigen::Matrix4f, counters as floats)."""
+    out = rows.astype(np.float32, copy=True)
+    out[:, 0:16] = rows[:, 0:16].reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1, 16)
+    out[:, 46:48] = rows[:, 46:48].copy().view(np.int32).astype(np.float32)
+    return out
+
+
+class DeviceRowGather:
+    """All-gather of the per-pair result rows that never leaves the device (NCCL over NVLink).
+
+    ``enqueue(solver)`` is called right after ``solver.launch()``: a 48-float-per-pair copy behind the solve on the solver's
+    own stream puts the rows into a staging slot, an event hands them to a side stream and ``all_gather_into_tensor`` fills
+    the slot's pre-allocated table there.  Nothing blocks the host, so the next batch is enqueued at once and the collective
+    overlaps it; ``table(slot)`` is the only synchronising call (one download of the gathered table).  Ranks hold the same
+    number of rows per slot (`rows_per_rank`, shorter shards are zero-padded)."""
+
+    def __init__(self, rows_per_rank: int, device, slots: int = 3):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.cap, self.device, self.slots = rows_per_rank, device, slots
+        self.stage = [torch.zeros((rows_per_rank, ROW), dtype=torch.float32, device=device) for _ in range(slots)]
+        self.tables = [torch.zeros((self.world * rows_per_rank, ROW), dtype=torch.float32, device=device) for _ in range(slots)]
+        self.side = torch.cuda.Stream(device=device)
+        self.done = [None] * slots
+        self.count = 0
+
+    def enqueue(self, solver, first: int = 0) -> int:
+        """`first`: leading rows of the solver's batch to leave out (the history halo pairs of a sharded sequence)."""
+        self.stage_rows(solver, first, None, 0)
+        return self.launch_gather()
+
+    def stage_rows(self, solver, first: int, n, at: int):
+        """Copy rows [first, first + n) of the solver's last batch into rows [at, at + n) of the current slot's staging buffer,
+        behind the solve on the solver's stream (several solver contexts may each contribute a part of one table)."""
+        torch = self.torch
+        slot = self.count % self.slots
+        st = torch.cuda.ExternalStream(solver.stream, device=self.device)
+        rows = solver.result_rows_device()
+        rows = rows[first:] if n is None else rows[first:first + n]
+        if self.done[slot] is not None:
+            st.wait_event(self.done[slot])  # the slot's previous table has been produced (and, by contract, read)
+        with torch.cuda.stream(st):
+            self.stage[slot][at: at + rows.shape[0]].copy_(rows, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(st)
+        self.side.wait_event(ready)
+
+    def launch_gather(self) -> int:
+        """One all-gather of the current slot (after every stage_rows of it); the same number of calls on every rank."""
+        torch = self.torch
+        slot = self.count % self.slots
+        self.count += 1
+        with torch.cuda.stream(self.side):
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.tables[slot], self.stage[slot])
+            else:
+                self.tables[slot].copy_(self.stage[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[slot] = ev
+        return slot
+
+    def table(self, slot: int, counts=None) -> np.ndarray:
+        """The gathered (world * rows_per_rank, 48) table of `slot` in the host row layout; `counts` = rows each rank really
+        holds (padding removed)."""
+        self.done[slot].synchronize()
+        t = self.tables[slot].cpu().numpy()
+        if counts is not None:
+            t = np.concatenate([t[r * self.cap: r * self.cap + n] for r, n in enumerate(counts)], axis=0)
+        return rows_from_device_layout(t)
+
+
 def compose_trajectory(T_colmajor: np.ndarray, start: np.ndarray | None = None) -> np.ndarray:
     """Prefix product of the increments: pose_k = pose_{k-1} @ T_k (float64), shape (n+1, 4, 4)."""
     n = T_colmajor.shape[0]
@@ -101,5 +177,11 @@ def solve_sequence_sharded(solver, depth, inten, device=None, want_images=False,
     # with the 5-frame history every rank re-solves the last four pairs of its predecessor instead of exchanging them
     halo = min(HISTORY_HALO, f0) if history else 0
     local = solver.solve_sequence(depth[f0 - halo:f1 + 1], inten[f0 - halo:f1 + 1], want_images=want_images, history=history, halo=halo)
-    table = gather_rows(pack_rows(local), n_frames - 1, device=device)
+    if device is not None and str(device).startswith("cuda"):
+        # rows stay on the device: staging copy behind the solve, NCCL all-gather on a side stream, one download
+        counts = [shard_pairs(n_frames - 1, r, world)[1] - shard_pairs(n_frames - 1, r, world)[0] for r in range(world)]
+        g = DeviceRowGather(max(counts), device, slots=1)
+        table = g.table(g.enqueue(solver, first=halo), counts)
+    else:
+        table = gather_rows(pack_rows(local), n_frames - 1, device=device)
     return unpack_rows(table), local

@@ -82,6 +82,7 @@ class StaticFusionSolver:
         self.params = params if params is not None else default_params()
         self.rows, self.cols = self.params.rows, self.params.cols
         self.max_batch = max_batch
+        self.device = device
         h = C.c_void_p()
         check(self.L.sf_create(C.byref(h), C.byref(self.params), device, max_batch, 1 if trace else 0))
         self.h = h
@@ -228,6 +229,10 @@ class StaticFusionSolver:
             _ip(r.irls_iters), _ip(r.status)))
         return r
 
+    def set_copy_streams(self, on: bool = True):
+        """Raw-frame uploads and result downloads on the context's own copy streams (sf_set_copy_streams)."""
+        check(self.L.sf_set_copy_streams(self.h, int(bool(on))))
+
     def set_history(self, on: bool):
         """Sequence solves also run computeResidualsAgainstPreviousImage for every pair with four predecessors."""
         check(self.L.sf_set_history(self.h, int(bool(on))))
@@ -366,6 +371,25 @@ class StaticFusionSolver:
         check(self.L.sf_get_step_stats(self.h, _ip(nv), _ip(it)))
         return nv, it
 
+    def kmeans_iterations(self) -> np.ndarray:
+        """Lloyd iterations kMeans3DCoord ran for every pair of the last solve (KMeans.cpp:167-228)."""
+        out = np.zeros(self._n, np.int32)
+        check(self.L.sf_get_kmeans_iterations(self.h, _ip(out)))
+        return out
+
+    def result_rows_device(self):
+        """The last solve's result rows where they lie in device memory, as a zero-copy (n_pairs, 48) float32 CUDA tensor:
+        T_odometry (16, ROW-major), twist_odometry_old (6), b_segm (24), IRLS iterations and status (int32 bit patterns).
+        Ordered after the solve on the context's stream; valid until the next upload / launch on this context."""
+        import torch
+        ptr, n, w = C.c_void_p(0), C.c_int(0), C.c_int(0)
+        check(self.L.sf_result_rows_device(self.h, C.byref(ptr), C.byref(n), C.byref(w)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value, w.value), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+
+        return torch.as_tensor(_View(), device=torch.device("cuda", self.device))
+
     # ---- introspection (parity tests) ----
     def debug_set_stop_step(self, step: int):
         check(self.L.sf_debug_set_stop_step(self.h, step))
@@ -405,7 +429,11 @@ class PipelinedSolver:
 
     HALO = 4  # pairs a chunk re-solves so that its first pairs see their 5-frame history
 
-    def __init__(self, params: SfParams | None = None, device: int = 0, chunk: int = 128, n_ctx: int = 3, history: bool = False):
+    def __init__(self, params: SfParams | None = None, device: int = 0, chunk: int = 128, n_ctx: int = 3, history: bool = False,
+                 on_launch=None, copy_streams: bool = True):
+        """on_launch(ctx, first_pair, n_pairs, halo): called right after a chunk's solve is enqueued (e.g. to enqueue a
+        device-side all-gather of its result rows, sharding.DeviceRowGather)."""
+        self.on_launch = on_launch
         self.params = params if params is not None else default_params()
         self.rows, self.cols = self.params.rows, self.params.cols
         self.chunk = chunk
@@ -413,6 +441,7 @@ class PipelinedSolver:
         self.ctx = [StaticFusionSolver(self.params, device=device, max_batch=chunk + (self.HALO if history else 0)) for _ in range(n_ctx)]
         for c in self.ctx:
             c.set_history(history)
+            c.set_copy_streams(copy_streams)
         self.pending = []  # (ctx, span, result) of the chunks in flight, oldest first
         self._turn = 0
 
@@ -421,11 +450,21 @@ class PipelinedSolver:
         for c in self.ctx:
             c.close()
 
+    def solve_sequence_raw(self, bgr, depth_raw, res_factor: int = 1, out: BatchResult | None = None, want_images: bool = True,
+                           wait: bool = True) -> BatchResult:
+        """solve_sequence for the inputs the reference's loader ingests (FrontEnd.cpp:216-254): decoded 8-bit colour
+        (n, H*rf, W*rf, 3) and 16-bit depth in millimetres (n, H*rf, W*rf), in file orientation; the flip, the decimation by
+        res_factor and the conversion to intensity / metres run on the device inside each chunk (sf_upload_sequence_raw)."""
+        return self._run(int(depth_raw.shape[0]) - 1, out, want_images, wait,
+                         lambda ctx, a, b: ctx.upload_sequence_raw(bgr[a:b], depth_raw[a:b], res_factor))
+
     def solve_sequence(self, depth, inten, out: BatchResult | None = None, want_images: bool = True, wait: bool = True) -> BatchResult:
         """wait=False returns as soon as every chunk is enqueued: the call overlaps the next one (its uploads and solves run
         while this one's results still travel back).  The caller keeps `depth` / `inten` unchanged and does not read the
         result until ``wait_for(result)`` or ``flush()``."""
-        n_pairs = int(depth.shape[0]) - 1
+        return self._run(int(depth.shape[0]) - 1, out, want_images, wait, lambda ctx, a, b: ctx.upload_sequence(depth[a:b], inten[a:b]))
+
+    def _run(self, n_pairs, out, want_images, wait, upload) -> BatchResult:
         r = out if out is not None else BatchResult(n_pairs, self.rows, self.cols, want_images)
         spans = [(s, min(s + self.chunk, n_pairs)) for s in range(0, n_pairs, self.chunk)]
         for s0, s1 in spans:
@@ -434,8 +473,10 @@ class PipelinedSolver:
             while any(p[0] is ctx for p in self.pending):  # this context is still busy with an older chunk: collect up to it
                 self._drain(self.pending.pop(0))
             halo = min(self.HALO, s0) if self.history else 0
-            ctx.upload_sequence(depth[s0 - halo:s1 + 1], inten[s0 - halo:s1 + 1])  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
+            upload(ctx, s0 - halo, s1 + 1)  # pairs s0..s1-1 need frames s0..s1 (one halo frame)
             ctx.launch()
+            if self.on_launch is not None:
+                self.on_launch(ctx, s0, s1 - s0, halo)
             ctx.download_range_begin(halo, s1 - s0, r, at=s0)  # the results start back as soon as the chunk is solved
             self.pending.append((ctx, (s0, s1, halo), r))
         if wait:

