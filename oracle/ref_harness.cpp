@@ -84,8 +84,15 @@ typedef struct {
     float previous_speed_const_weight, previous_speed_eig_weight;
 } ref_params;
 
+#ifdef SF_B200_BINDING  /* the library built from ref_binding.cpp: the class's solver methods forward to libstaticfusion_b200.so */
+void ref_binding_release(void* h);
+int ref_is_b200_binding(void) { return 1; }
+#else
+static void ref_binding_release(void*) {}
+int ref_is_b200_binding(void) { return 0; }
+#endif
 void* ref_create(int res_factor) { return new StaticFusion((unsigned)res_factor); }
-void ref_destroy(void* h) { delete static_cast<StaticFusion*>(h); }
+void ref_destroy(void* h) { ref_binding_release(h); delete static_cast<StaticFusion*>(h); }
 int ref_rows(void* h) { return (int)static_cast<StaticFusion*>(h)->rows; }
 int ref_cols(void* h) { return (int)static_cast<StaticFusion*>(h)->cols; }
 int ref_default_levels(void* h) { return (int)static_cast<StaticFusion*>(h)->ctf_levels; }
@@ -162,6 +169,7 @@ double ref_assoc_entry(int k, char* depth_path, char* color_path, int cap) {
     return g_assoc_ts[k];
 }
 
+#ifndef SF_B200_BINDING  /* stage-by-stage entry points into the reference's own solver code (absent from the bound library) */
 void ref_kmeans(void* h) { StaticFusion& s = *static_cast<StaticFusion*>(h); s.kMeans3DCoord(); s.createClustersPyramidUsingKMeans(); }
 /* one warp of pyramid level `image_level` with the current T_odometry (FrontEnd.cpp:775) */
 void ref_warp_level(void* h, int image_level) {
@@ -186,6 +194,7 @@ void ref_linearise_level(void* h, int level_i, int first) {
     s.calculateCoord(); s.calculateDerivatives(); s.computeWeights(); s.computeSegPrior();
 }
 void ref_solve_level(void* h) { static_cast<StaticFusion*>(h)->solveOdometryAndSegmJoint(); }
+#endif
 
 /* state readers (row-major out) */
 int ref_get_image(void* h, const char* name, int L, float* out) {

@@ -379,6 +379,8 @@ public:
     T& operator[](Index k) { return m.a[(size_t)k]; }
     const T& operator[](Index k) const { return m.a[(size_t)k]; }
     void fill(T v) { m.fill(v); }
+    T* data() { return m.data(); }
+    const T* data() const { return m.data(); }
     T sum() const { return m.sum(); }
     const Dense<T>& matrix() const { return m; }
     template <class U> ArrayD<U> cast() const { return ArrayD<U>(m.template cast<U>()); }

@@ -15,6 +15,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libsf_ref.so")
+# the reference's own class with the forwarding binding of INTEGRATION.md compiled in (oracle/ref_binding.cpp): its solver
+# methods call libstaticfusion_b200.so; none of the reference's solver code is inside
+BOUND_LIB_PATH = os.path.join(_HERE, "_ref", "libsf_ref_b200.so")
 REFERENCE_DIR = "/root/reference"
 NUM_CLUSTERS = 24
 
@@ -35,18 +38,22 @@ def build() -> str | None:
     """Compile from the reference tree when it is present; otherwise keep whatever prebuilt library exists."""
     if os.path.isdir(REFERENCE_DIR):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE_DIR}"])
+        if os.path.exists(os.path.join(_HERE, "..", "staticfusion_b200", "lib", "libstaticfusion_b200.so")):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref_b200", f"REF={REFERENCE_DIR}"])
     return LIB_PATH if os.path.exists(LIB_PATH) else None
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(bound: bool = False):
+    if bound not in _libs:
         if build() is None:
             raise FileNotFoundError(LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+        path = BOUND_LIB_PATH if bound else LIB_PATH
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = C.CDLL(path)
         fp, vp = C.POINTER(C.c_float), C.c_void_p
         L.ref_create.restype = vp
         L.ref_create.argtypes = [C.c_int]
@@ -68,10 +75,11 @@ def lib():
         L.ref_get_per_cluster_average_residual.argtypes = [vp, fp]
         L.ref_get_residual_image.argtypes = [vp, C.c_char_p, fp]
         L.ref_get_residual_image.restype = C.c_int
-        L.ref_kmeans.argtypes = [vp]
-        L.ref_warp_level.argtypes = [vp, C.c_int]
-        L.ref_linearise_level.argtypes = [vp, C.c_int, C.c_int]
-        L.ref_solve_level.argtypes = [vp]
+        if not bound:  # stage-by-stage entry points into the reference's own solver code
+            L.ref_kmeans.argtypes = [vp]
+            L.ref_warp_level.argtypes = [vp, C.c_int]
+            L.ref_linearise_level.argtypes = [vp, C.c_int, C.c_int]
+            L.ref_solve_level.argtypes = [vp]
         L.ref_get_image.argtypes = [vp, C.c_char_p, C.c_int, fp]
         L.ref_get_image.restype = C.c_int
         L.ref_get_labels.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
@@ -82,8 +90,9 @@ def lib():
         L.ref_load_image_from_sequence_assoc.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
         L.ref_load_image_from_sequence_assoc.restype = C.c_int
         L.ref_get_current.argtypes = [vp, fp, fp, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)]
-        _lib = L
-    return _lib
+        assert L.ref_is_b200_binding() == int(bound)
+        _libs[bound] = L
+    return _libs[bound]
 
 
 def _fp(a):
@@ -97,8 +106,9 @@ def _f32(a):
 class Reference:
     """`class StaticFusion` of the reference (res_factor 1, 2, 4, 8 -> 640x480 ... 80x60), driver parameters by default."""
 
-    def __init__(self, res_factor: int = 2, **params):
-        self.L = lib()
+    def __init__(self, res_factor: int = 2, bound: bool = False, **params):
+        """bound=True: the same class with INTEGRATION.md's binding compiled in (solver calls run on the GPU)."""
+        self.L = lib(bound)
         self.h = self.L.ref_create(res_factor)
         self.rows, self.cols = self.L.ref_rows(self.h), self.L.ref_cols(self.h)
         p = dict(ctf_levels=self.L.ref_default_levels(self.h), max_iter_per_level=3, max_iter_irls=6, use_motion_filter=1,

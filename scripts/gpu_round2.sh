@@ -3,8 +3,8 @@
 TAG=${TAG:-r2}
 NG=${NG:-$(nvidia-smi -L | wc -l)}
 mkdir -p gpurun_out
-if [ -z "$SKIP_TESTS" ]; then python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/${TAG}_pytest.log; fi
-python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench n1 exit $?"
+if [ -z "$SKIP_TESTS" ]; then python -m pytest ${TESTS:-tests} -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/${TAG}_pytest.log; fi
+if [ -z "$SKIP_N1" ]; then python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench n1 exit $?"; fi
 tail -3 gpurun_out/${TAG}_bench_n1.err
 if [ "$NG" -gt 1 ]; then
   for cfg in 2 4; do

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     int run_lab = -1, run_size = 0, run_nonnull = 0;
     long long run_prior = 0;
     int cur_pair = -1, items_since_fold = 0;
+    int cur_slot = -1, slot_pair = -1;  // the pair of the current slot stays in a register: one dependent global load per pair, not per item
 
     // fold the block's partial reductions into the pair's cells (block-collective) and reset them
     auto flush = [&](int pair) {
@@ -186,7 +187,13 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
 
   for (int item = item0; item < item1; item++) {
     const int slot = item / blocks_per_pair;
-    const int pair = a.active_list[slot];
+    if (slot != cur_slot) { cur_slot = slot; slot_pair = a.active_list[slot]; }
+    const int pair = slot_pair;
+    // this thread's four labels: issued before the wait for the staged planes, so that their latency hides behind it
+    const int chunk = (item - slot * blocks_per_pair) * SF_LIN_THREADS + tid;
+    const bool inb = chunk < (g.P >> 2);
+    uchar4 l4 = make_uchar4(LABEL_NONE, LABEL_NONE, LABEL_NONE, LABEL_NONE);
+    if (inb) l4 = __ldg(reinterpret_cast<const uchar4*>(a.labels + (size_t)pair * a.pyr_stride + g.off + ((size_t)chunk << 2)));
     if (pair != cur_pair || items_since_fold == 128) {  // block-uniform
         if (cur_pair >= 0) flush(cur_pair);
         cur_pair = pair;
@@ -211,9 +218,6 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     }
     const float* const sp = stage_mem + (size_t)st * 4 * span - st_lo;  // plane q of this item: sp[q * span + pixel]
     items_since_fold++;
-    const int nchunks = g.P >> 2;
-    const int chunk = (item - slot * blocks_per_pair) * SF_LIN_THREADS + tid;
-    const bool inb = chunk < nchunks;
     {   // pad pixels of the level's last, partial tile: stale labels of a finer level must not be read as valid
         const int padded = (int)tiles_per_pair((size_t)g.P) * (ROW_TILE / 4);
         if (!inb && chunk < padded) {
@@ -229,7 +233,6 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     // the very first step uses the prediction level itself as the warped image (FrontEnd.cpp:1103-1110)
     const float* wdp = first ? a.pyr_d + (size_t)fp * a.pyr_stride + g.off : a.warp_d + (size_t)pair * a.P0;
     const float* wip = first ? a.pyr_i + (size_t)fp * a.pyr_stride + g.off : a.warp_i + (size_t)pair * a.P0;
-    const uint8_t* lab = a.labels + (size_t)pair * a.pyr_stride + g.off;
     uint8_t* tiles = a.tiles + (size_t)pair * tiles_per_pair(a.P0) * TILE_BYTES;
     float* dbg = a.dbg ? a.dbg + (size_t)pair * NPLANES * a.P0 : nullptr;
     // plane q (0 depth, 1 intensity of the current frame; 2, 3 of the warped one) at pixel px: staged copy or global memory
@@ -292,7 +295,6 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
                 ID[j] = 0.5f * (di4[j] + dwi4[j]);
             }
         }
-        const uchar4 l4 = __ldg(reinterpret_cast<const uchar4*>(lab + p0));
         const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
         float ro[NROWPL][2];  // rows of a pixel pair, stored as float2 (8 B per lane: full sectors)
         unsigned char ovl[4];
