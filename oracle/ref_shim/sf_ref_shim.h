@@ -213,6 +213,9 @@ public:
     void swap(Dense& o) { std::swap(r_, o.r_); std::swap(c_, o.c_); a.swap(o.a); }
     Dense replicate(int, int) const { return *this; }
     Dense eval() const { return *this; }
+    /* corner blocks as copies (the trajectory writers read them: Datasets.cpp:258, Reconstruction.cpp:472-473) */
+    Dense topLeftCorner(Index r, Index c) const { Dense o((int)r, (int)c); for (int j = 0; j < (int)c; j++) for (int i = 0; i < (int)r; i++) o(i, j) = (*this)(i, j); return o; }
+    Dense topRightCorner(Index r, Index c) const { Dense o((int)r, (int)c); for (int j = 0; j < (int)c; j++) for (int i = 0; i < (int)r; i++) o(i, j) = (*this)(i, c_ - (int)c + j); return o; }
 
     /* reductions: sequential, column-major */
     T sum() const { T s = 0; for (size_t k = 0; k < a.size(); k++) s += a[k]; return s; }
@@ -437,6 +440,34 @@ typedef Matrix<float, Dynamic, Dynamic> MatrixXf;
 typedef Matrix<int, Dynamic, Dynamic> MatrixXi;
 typedef Matrix<float, Dynamic, 1> VectorXf;
 typedef Matrix<float, 2, 2> Matrix2f;
+/* Eigen::Quaternionf(Matrix3f): stand-in for Eigen's rotation-matrix constructor (QuaternionBase::operator=(MatrixBase), the
+ * trace / largest-diagonal branches of Eigen/src/Geometry/Quaternion.h), float arithmetic */
+class Quaternionf {
+    float q_[4];  /* x, y, z, w */
+public:
+    explicit Quaternionf(const Dense<float>& m) {
+        float t = m(0, 0) + m(1, 1) + m(2, 2);
+        if (t > 0.f) {
+            t = std::sqrt(t + 1.f);
+            q_[3] = 0.5f * t;
+            t = 0.5f / t;
+            q_[0] = (m(2, 1) - m(1, 2)) * t; q_[1] = (m(0, 2) - m(2, 0)) * t; q_[2] = (m(1, 0) - m(0, 1)) * t;
+        } else {
+            int i = 0;
+            if (m(1, 1) > m(0, 0)) i = 1;
+            if (m(2, 2) > m(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.f);
+            q_[i] = 0.5f * t;
+            t = 0.5f / t;
+            q_[3] = (m(k, j) - m(j, k)) * t; q_[j] = (m(j, i) + m(i, j)) * t; q_[k] = (m(k, i) + m(i, k)) * t;
+        }
+    }
+    float x() const { return q_[0]; }
+    float y() const { return q_[1]; }
+    float z() const { return q_[2]; }
+    float w() const { return q_[3]; }
+};
 typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<float, 3, 1> Vector3f;

@@ -37,7 +37,7 @@ def available() -> bool:
 def build() -> str | None:
     """Compile from the reference tree when it is present; otherwise keep whatever prebuilt library exists."""
     if os.path.isdir(REFERENCE_DIR):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE_DIR}"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "ref_traj", f"REF={REFERENCE_DIR}"])
         if os.path.exists(os.path.join(_HERE, "..", "staticfusion_b200", "lib", "libstaticfusion_b200.so")):
             subprocess.check_call(["make", "-C", _HERE, "-s", "ref_b200", f"REF={REFERENCE_DIR}"])
     return LIB_PATH if os.path.exists(LIB_PATH) else None

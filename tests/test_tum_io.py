@@ -196,6 +196,68 @@ def test_trajectory_writers_python_equals_cpp(tmp_path):
     assert (tmp_path / "run.freiburg").read_text() == tr.freiburg_text()
 
 
+def _writers_on(poses, ts_obs, t_us, ddt, tmp_path):
+    """(Datasets text, .freiburg text) of the Python and of the C++ writer for a list of composed poses."""
+    from staticfusion_b200 import tum_io
+    tr = tum_io.Trajectory()
+    lines, inp = [], []
+    prev = np.eye(4, dtype=np.float32)
+    for P, a, b, c in zip(poses, ts_obs, t_us, ddt):
+        tr.currPose = P.astype(np.float32).copy()  # the writers see the composed pose (Reconstruction.cpp:256,265 forms it)
+        tr.poseGraph.append(tr.currPose.copy()); tr.poseLogTimes.append(int(b))
+        ln = tr.dataset_line(float(a), float(c))
+        if ln:
+            lines.append(ln)
+    return "".join(lines), tr.freiburg_text()
+
+
+def test_trajectory_writers_match_the_reference_fixture(tmp_path):
+    """Text of Datasets::writeTrajectoryFile (Datasets.cpp:252-266) and of savePly's pose graph (Reconstruction.cpp:460-485)
+    as THE REFERENCE'S OWN code writes it (tests/golden/reference_trajectory.npz, made by make_trajectory_golden.py from the
+    reference sources compiled against the shim): separators, precision, the skipped line, both quaternion branches."""
+    g = np.load(os.path.join(GOLDEN, "reference_trajectory.npz"))
+    dataset_txt, freiburg_txt = _writers_on(g["poses"], g["ts_obs"], g["t_us"], g["ddt"], tmp_path)
+    assert dataset_txt == str(g["dataset_txt"]) and freiburg_txt == str(g["freiburg_txt"])
+    assert len(dataset_txt.splitlines()) == len(g["poses"]) - 1  # one frame repeats its depth image (Datasets.cpp:255)
+
+
+def test_trajectory_cpp_writer_matches_the_reference_fixture(tmp_path):
+    """The C++ host twin (TumIO.hpp, via tum_io_tool) on the increments that compose the fixture's poses."""
+    from make_trajectory_golden import trajectory_inputs
+    from staticfusion_b200 import tum_io
+    g = np.load(os.path.join(GOLDEN, "reference_trajectory.npz"))
+    # regenerate the increments (same seed) and check that they compose to the stored poses
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    inp, P = [], np.eye(4, dtype=np.float32)
+    for k in range(len(g["poses"])):
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = Rotation.from_rotvec(rng.normal(size=3) * (0.02 if k % 7 else 2.5)).as_matrix().astype(np.float32)
+        T[:3, 3] = rng.normal(size=3).astype(np.float32) * 0.01
+        P = tum_io.pose_compose(P, T)
+        assert np.array_equal(P, g["poses"][k])
+        inp.append("%d %.17g %.9g " % (int(g["t_us"][k]), float(g["ts_obs"][k]), float(g["ddt"][k])) + " ".join("%.9g" % x for x in T.T.reshape(16)))
+    f = tmp_path / "traj_in.txt"
+    f.write_text("\n".join(inp) + "\n")
+    out = subprocess.run([host_tool("tum_io_tool"), "traj", str(f)], capture_output=True, text=True, check=True).stdout
+    cpp_dataset, cpp_freiburg = out.split("--\n")
+    assert cpp_dataset == str(g["dataset_txt"]) and cpp_freiburg == str(g["freiburg_txt"])
+    assert trajectory_inputs is not None
+
+
+def test_trajectory_writers_match_the_live_reference(tmp_path):
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "ref_traj")
+    if not os.path.exists(ref_tool) and not os.path.isdir("/root/reference"):
+        pytest.skip("oracle/_ref/ref_traj is not present and /root/reference is not mounted")
+    from make_trajectory_golden import run_reference, trajectory_inputs
+    poses, ts_obs, t_us, ddt = trajectory_inputs(n=30, seed=21)
+    ref_dataset, ref_freiburg = run_reference(poses, ts_obs, t_us, ddt) if os.path.isdir("/root/reference") else (None, None)
+    if ref_dataset is None:
+        pytest.skip("needs the reference tree to rebuild the tool")
+    dataset_txt, freiburg_txt = _writers_on(poses, ts_obs, t_us, ddt, tmp_path)
+    assert dataset_txt == ref_dataset and freiburg_txt == ref_freiburg
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 def sequence_as_files(depth, inten, rf, seed=0):
     """Full-resolution decoded images whose loader output is (close to) the given float frames: grey BGR, millimetre
