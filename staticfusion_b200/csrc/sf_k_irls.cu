@@ -803,16 +803,10 @@ void pass_kernel_attrs_impl() {  // per device (function attributes are not shar
     cudaFuncSetAttribute(irls_fused_kernel<FW_SMALL, FB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem(FW_SMALL));
 }
 
-// grid of a pass launch: the resident blocks, or fewer when even the finest partition of every pair has fewer items.  From
-// the third IRLS iteration on most pairs have left the loop (the drivers' threshold ends it after 2-3 iterations for ~95 % of
-// the pairs) and many launches find no pair at all: those launches get a quarter of the grid, which costs half as much when
-// it is empty and still holds one block per SM quadrant when a few pairs go on (the items are handed out dynamically).
-static inline int pass_cap(const Arena& a, int it) {
+// grid of a pass launch: the resident blocks, or fewer when even the finest partition of every pair has fewer items
+// (measured: a quarter-size grid for the late, mostly empty iterations costs the same - an empty launch is launch-bound)
+static inline int pass_grid(const Arena& a, int P, int n_pairs) {
     const int cap = a.num_sms * PS_BLOCKS_PER_SM;
-    return it >= 4 ? (cap + 3) / 4 : cap;
-}
-static inline int pass_grid(const Arena& a, int P, int n_pairs, int it) {
-    const int cap = pass_cap(a, it);
     const int tiles = (int)tiles_per_pair((size_t)P);
     const int most = tiles / (4 * PS_WARPS) > 1 ? tiles / (4 * PS_WARPS) : 1;
     const long long total = (long long)most * n_pairs;
@@ -820,8 +814,7 @@ static inline int pass_grid(const Arena& a, int P, int n_pairs, int it) {
 }
 int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, int, int, int it, const LaunchCfg& c) {
     const int slot = (*c.next_ctr)++ % MAX_WORK_CTRS;
-    const int grid = pass_grid(a, g.P, c.n_pairs, it);
-    irls_pass1_kernel<<<grid, PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, it, pass_cap(a, it), tile_pattern(g.cols), slot);
+    irls_pass1_kernel<<<pass_grid(a, g.P, c.n_pairs), PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, it, a.num_sms * PS_BLOCKS_PER_SM, tile_pattern(g.cols), slot);
     return 1;
 }
 
@@ -842,8 +835,7 @@ int launch_irls_fused(const Arena& a, const DevParams& p, const LevelGeom& g, in
 
 int launch_irls_pass2(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c) {
     const int slot = (*c.next_ctr)++ % MAX_WORK_CTRS;
-    const int grid = pass_grid(a, g.P, c.n_pairs, it);
-    irls_pass2_kernel<<<grid, PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, level_i, k, it, pass_cap(a, it), tile_pattern(g.cols), slot);
+    irls_pass2_kernel<<<pass_grid(a, g.P, c.n_pairs), PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, level_i, k, it, a.num_sms * PS_BLOCKS_PER_SM, tile_pattern(g.cols), slot);
     return 1;
 }
 
