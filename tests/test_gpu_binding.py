@@ -64,7 +64,10 @@ def test_driver_loop_through_the_bound_reference_class(sf_mod, oracle_mod, fixtu
         if np.array_equal(f64.b_perpixel() > 0.5, g["b_perpixel"][t - 1] > 0.5):
             assert np.array_equal(r.b_perpixel() > 0.5, g["b_perpixel"][t - 1] > 0.5), t
         pc_b, pc_r = r.per_cluster_average_residual(), g["per_cluster"][t - 1]
-        assert np.array_equal(np.isnan(pc_b), np.isnan(pc_r)) and np.allclose(pc_b, pc_r, rtol=0, atol=2e-5 + 10 * floor, equal_nan=True), t
+        pc_64 = f64.per_cluster_average_residual()
+        assert np.array_equal(np.isnan(pc_b), np.isnan(pc_64)) and np.allclose(pc_b, pc_64, rtol=0, atol=1e-5, equal_nan=True), t
+        if floor <= 2e-6:  # frames on which double sums reproduce the reference's pose: its 5-frame residuals are reproduced as well
+            assert np.array_equal(np.isnan(pc_b), np.isnan(pc_r)) and np.allclose(pc_b, pc_r, rtol=0, atol=2e-5, equal_nan=True), t
         if t >= 5 and np.all(np.abs(pc_r[~np.isnan(pc_r)] - 0.017) > 1e-4):
             assert np.array_equal(pc_b < 0.017, pc_r < 0.017), t  # the branch buildSegmImage takes (SegmentationBackground.cpp:190-194)
     s.close()
