@@ -7,7 +7,7 @@ if [ -z "$SKIP_TESTS" ]; then python -m pytest ${TESTS:-tests} -m gpu -x -q > gp
 if [ -z "$SKIP_N1" ]; then python bench.py --steps ${STEPS:-10} --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench n1 exit $?"; fi
 tail -3 gpurun_out/${TAG}_bench_n1.err
 if [ "$NG" -gt 1 ]; then
-  for cfg in 2 4; do
+  for cfg in ${CFGS:-2 4}; do
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NG --steps ${STEPS:-10} --warmup 3 --config $cfg --no-cpu-baseline > gpurun_out/${TAG}_bench_c${cfg}_n${NG}.json 2> gpurun_out/${TAG}_bench_c${cfg}_n${NG}.err; echo "bench config $cfg n$NG exit $?"
     tail -3 gpurun_out/${TAG}_bench_c${cfg}_n${NG}.err
   done
