@@ -98,7 +98,7 @@ def pair_indices(n_pairs, n_distinct):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the warm-up steps through the timed region (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -110,7 +110,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -417,12 +417,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)  # sampled from the warm-up steps (same kernels, same load) to the end of the timed region
+    clocks.start()
     for k in range(max(a.warmup, 3)):
         device_step(ctxs[k % len(ctxs)])
     barrier()
     # --- timed region: EXACTLY K steps, device-timed on the library's stream(s) (CUDA-graph replay of the schedule)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     e_side = torch.cuda.Event(enable_timing=True)
