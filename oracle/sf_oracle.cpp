@@ -9,12 +9,13 @@
  * but every loop keeps the reference's traversal order (u outer, v inner = Eigen
  * column-major order) because that order defines the float summation order.
  *
- * Two accumulation policies (sf_oracle.h):
+ * Three accumulation policies (sf_oracle.h):
  *   ORC_ACCUM_F32   reference-literal sequential float sums, float small algebra.
- *   ORC_ACCUM_EXACT order-independent fixed-point sums where magnitudes are bounded
- *                   (k-means centres, warp splat, seg prior, mean|B|, per-label residuals),
- *                   double sums elsewhere (normal equations, |res|^2), double small algebra.
+ *   ORC_ACCUM_EXACT every cross-pixel sum is an order-independent fixed-point (integer) sum: k-means centres,
+ *                   warp splat, seg prior, mean|B|, per-label residuals, and the normal equations / |res|^2
+ *                   (products rounded to 2^-40 of the column-bound product); double small algebra.
  *                   This is the numerics contract of the CUDA path.
+ *   ORC_ACCUM_F64   like EXACT but plain double sums for the normal equations / |res|^2: the yardstick.
  *
  * Third-party arithmetic that is NOT in the reference tree (Eigen LDLT / inverse /
  * SelfAdjointEigenSolver / colPivHouseholderQr / matrix exp+log, MRPT CPose3D) is

@@ -3,8 +3,8 @@
 // Numerics contract: every per-pixel expression is evaluated in float32
 // with the operation order of the reference source and no FMA contraction (the library is
 // compiled with -fmad=false; fused adds are written explicitly where the contract allows).
-// Cross-pixel sums are either order-independent fixed-point integers or fixed-tree double
-// sums; the 6x6 / 24x24 solves, the 6x6 eigen-decomposition and SE(3) exp/log run in
+// Every cross-pixel sum is an order-independent fixed-point (integer) sum - the normal equations
+// through double-precision FMAs onto accumulators whose bit patterns are those integers; the 6x6 / 24x24 solves, the 6x6 eigen-decomposition and SE(3) exp/log run in
 // double on one thread / one warp per pair.
 #pragma once
 #include <cuda_runtime.h>
