@@ -60,7 +60,7 @@ struct sf_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     // the static schedule captured once per (batch shape, stop step) and replayed: removes ~500 launch gaps per solve
-    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history, lanes; cudaGraphExec_t exec; int launches; };
+    struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history, lanes, prof; cudaGraphExec_t exec; int launches; std::vector<ProfRec> prof_recs; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
     int fused_max_tiles = 300;  // levels with at most this many 64-pixel tiles per pair run the fused IRLS kernel (SF_FUSED_MAX_TILES)
@@ -104,18 +104,28 @@ static cudaEvent_t prof_event(sf_ctx* c) {
     }
     return c->ev_pool[c->ev_used++];
 }
+// One event pair per kernel group.  With profiling on, the schedule is still captured and replayed as a CUDA graph (on one
+// stream, so that the groups do not overlap): the events are recorded as EXTERNAL event nodes of the graph, i.e. the times
+// are those of the product's own execution mode, without the host-side launch gaps plain launches would add to every
+// small kernel.
 struct ProfScope {
     sf_ctx* c;
     bool on;
     cudaEvent_t e1;
+    static void record(sf_ctx* c, cudaEvent_t e) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(c->stream, &st);
+        if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, c->stream, cudaEventRecordExternal);
+        else cudaEventRecord(e, c->stream);
+    }
     ProfScope(sf_ctx* ctx, int cls, int level) : c(ctx), on(ctx->prof_on), e1(nullptr) {
         if (!on) return;
         cudaEvent_t e0 = prof_event(c);
         e1 = prof_event(c);
-        cudaEventRecord(e0, c->stream);
+        record(c, e0);
         c->prof.push_back({cls, level, e0, e1});
     }
-    ~ProfScope() { if (on) cudaEventRecord(e1, c->stream); }
+    ~ProfScope() { if (on) record(c, e1); }
 };
 
 static void fill_dev_params(sf_ctx* c) {
@@ -529,12 +539,14 @@ static int enqueue_solve(sf_ctx* c, bool build_pyramids) {
 }
 
 static int launch_solve(sf_ctx* c, bool build_pyramids) {
-    if (c->prof_on || !c->use_graph) return enqueue_solve(c, build_pyramids);  // per-kernel events need plain launches
+    static const bool prof_plain = std::getenv("SF_PROF_PLAIN") != nullptr;  // A-B: per-kernel events around plain launches
+    if (!c->use_graph || (c->prof_on && prof_plain)) return enqueue_solve(c, build_pyramids);
     for (const auto& g : c->graphs)
         if (g.n_pairs == c->n_pairs && g.n_frames == c->n_frames && g.stop_step == c->stop_step && g.pyramids == (int)build_pyramids &&
-            g.history == (c->history && c->is_sequence) && g.lanes == choose_lanes(c)) {
+            g.history == (c->history && c->is_sequence) && g.lanes == choose_lanes(c) && g.prof == (int)c->prof_on) {
             CU(cudaGraphLaunch(g.exec, c->stream));
             c->launches = g.launches;
+            if (c->prof_on) c->prof = g.prof_recs;  // the graph's external event nodes: re-recorded by this replay
             return SF_OK;
         }
     cudaGraph_t graph = nullptr;
@@ -547,7 +559,8 @@ static int launch_solve(sf_ctx* c, bool build_pyramids) {
     const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e2 != cudaSuccess) return fail(SF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2));
-    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, (int)(c->history && c->is_sequence), choose_lanes(c), exec, c->launches});
+    c->graphs.push_back({c->n_pairs, c->n_frames, c->stop_step, (int)build_pyramids, (int)(c->history && c->is_sequence), choose_lanes(c), (int)c->prof_on, exec,
+                         c->launches, c->prof_on ? c->prof : std::vector<sf_ctx::ProfRec>()});
     CU(cudaGraphLaunch(exec, c->stream));
     return SF_OK;
 }
