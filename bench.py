@@ -11,13 +11,13 @@ loader ingests (FrontEnd.cpp:216-254): 8-bit colour + 16-bit depth in millimetre
 * metric  (BASELINE.json): QVGA solver iterations / s.  One iteration = one pass of the IRLS loop body
   (FrontEnd.cpp:611-684) at the finest level of the config; iterations at coarser levels are counted as
   finest-level equivalents by their valid-pixel ratio.  frames/s is reported alongside.
-* value   : raw frames already resident in HBM, device-timed (CUDA events on the library's streams, max over ranks); two
-            solver contexts alternate on consecutive steps (run.device_contexts), K steps timed as a whole.
+* value   : raw frames already resident in HBM, device-timed (CUDA events on the library's streams, max over ranks); four
+            solver contexts take turns on consecutive steps (run.device_contexts), K steps timed as a whole.
 * e2e     : the same batch through the public API (PipelinedSolver) with pinned HOST buffers: H2D of the raw frames,
             solve, D2H of poses + per-pixel static weights + labels, all inside the timed region.
-* roofline: SURVEY §8(d)'s unit, one IRLS iteration at the finest level = irls_pass1_kernel + irls_pass2_kernel: 96 B per
-            valid pixel per iteration over the CUDA-event time of ALL scheduled launches of the two kernels (empty ones
-            included), against the measured HBM peak in MEASURED_PEAKS.json; `kernels` holds the same fraction for every
+* roofline: SURVEY §8(d)'s unit, the IRLS iterations at the finest level (irls_loop_kernel: pass 1 + pass 2 of every
+            iteration of every pair, one launch per step): 96 B per valid pixel per iteration over the CUDA-event time of ALL
+            launches of the kernel, against the measured HBM peak in MEASURED_PEAKS.json; `kernels` holds the same fraction for every
             stage of the step (linearise 61 B/px, warp 40 B/px, k-means, pyramids ...) and `whole_step` the step's total
             algorithmic bytes over ms_per_step.
 * cpu_baseline / --impl reference: the CPU oracle's reference-literal policy (a plain-loop port that is pinned bit for bit
@@ -396,9 +396,11 @@ def main():
     p = sf.default_params(rows, cols, ctf_levels=levels)
     geom_P = [(rows >> l) * (cols >> l) for l in range(levels)]
 
-    # Two solver contexts take turns on consecutive steps: the latency-bound head of step k+1 (pyramids, k-means) runs beside the
-    # streaming tail of step k.  Every step is a complete pass over its own batch; the K steps are timed as a whole.
-    n_dev_ctx = int(os.environ.get("SF_BENCH_CTXS", "2"))
+    # Several solver contexts take turns on consecutive steps: the latency-bound parts of one step (k-means, the serial per-step
+    # kernels, the thin end of an IRLS loop) run beside the streaming kernels of the others.  Every step is a complete pass over
+    # its own batch; the K steps are timed as a whole.
+    # measured on one B200 (512 QVGA pairs, one lane): 2 / 3 / 4 / 5 / 6 contexts = 5.10 / 5.07 / 4.99 / 4.92 / 4.91 ms per step
+    n_dev_ctx = int(os.environ.get("SF_BENCH_CTXS", "4"))
     ctxs = [sf.StaticFusionSolver(p, device=local_rank, max_batch=n_batch) for _ in range(n_dev_ctx)]
     for x in ctxs:
         x.set_history(history)
@@ -558,18 +560,22 @@ def main():
                 e["note"] = note
             return e
 
-        pm = prof_ms / a.steps  # ms per step per (class, level), one stream, plain launches
-        kernels = {
-            "irls_iteration_finest (irls_pass1_kernel + irls_pass2_kernel, all scheduled launches)": entry(alg["irls_finest"], pm[5, 0] + pm[6, 0]),
-            "irls_pass1_kernel finest": entry(alg["irls_finest"] / 2, pm[5, 0]),
-            "irls_pass2_kernel finest": entry(alg["irls_finest"] / 2, pm[6, 0]),
+        pm = prof_ms / a.steps  # ms per step per (class, level): external event nodes of the graph, one stream
+        loop_mode = prof_n[6, 0] == 0  # irls_loop_kernel: one launch per step runs every iteration's pass 1 and pass 2 (class 5)
+        irls_name = ("irls_iteration_finest (irls_loop_kernel: pass 1 + pass 2 of every iteration, one launch per step)" if loop_mode else
+                     "irls_iteration_finest (irls_pass1_kernel + irls_pass2_kernel, all scheduled launches)")
+        kernels = {irls_name: entry(alg["irls_finest"], pm[5, 0] + pm[6, 0])}
+        if not loop_mode:
+            kernels["irls_pass1_kernel finest"] = entry(alg["irls_finest"] / 2, pm[5, 0])
+            kernels["irls_pass2_kernel finest"] = entry(alg["irls_finest"] / 2, pm[6, 0])
+        kernels.update({
             "irls_fused_kernel (coarser levels, whole IRLS loop of a pair per block)": entry(alg["irls_coarser"], float(pm[5, 1:].sum() + pm[6, 1:].sum())),
             "clustering (kmeans_kernel + label_connect_kernel + label_pyr_kernel)": entry(alg["clustering"], float(pm[2].sum()),
                                                                                        "12 B per level-1 pixel per Lloyd iteration actually run + 16 B per level-0 pixel"),
             "pyramid (pyr_down_kernel)": entry(alg["pyramid"], float(pm[1].sum())),
             "pose_update_kernel": entry(0.0, float(pm[7].sum()), "latency-bound serial algebra, no pixel traffic"),
             "finish + segm_image" + (" + history" if history else ""): entry(alg["segm_image"] + alg["history"], float(pm[8].sum())),
-        }
+        })
         for L in sorted(alg["linearise"]):
             kernels[f"linearise_kernel L{L}"] = entry(alg["linearise"][L], float(pm[4, L]))
         for L in sorted(alg["warp"]):
@@ -579,29 +585,31 @@ def main():
         for e in kernels.values():
             for k in ("achieved", "frac", "ms_per_step"):
                 e[k] = round(e[k], 4)
-        # launch-by-launch view of the finest-level IRLS iterations (the static schedule enqueues max_iter_per_level x max_iter_irls
-        # launches of each pass per step; a launch whose pairs have all left the IRLS loop returns after one load)
+        # the finest-level IRLS iterations of a step: how many pairs run each (the schedule allows max_iter_per_level outer steps x
+        # max_iter_irls iterations; pairs leave the loop on their own exit tests)
         steps_fine = [st for st in range(nv.shape[1]) if st // mipl == levels - 1]
         n_sched = len(steps_fine) * p.max_iter_irls
         per_launch = []
-        if all(len(x[0]) == n_sched and len(x[1]) == n_sched for x in pass_fine_ms):
+        timed = (not loop_mode) and all(len(x[0]) == n_sched and len(x[1]) == n_sched for x in pass_fine_ms)
+        if timed:
             l1 = np.stack([x[0] for x in pass_fine_ms]).mean(axis=0)
             l2 = np.stack([x[1] for x in pass_fine_ms]).mean(axis=0)
-            for j in range(n_sched):
-                st, itn = steps_fine[j // p.max_iter_irls], j % p.max_iter_irls + 1
-                act = it[:, st] >= itn
-                per_launch.append({"outer": j // p.max_iter_irls, "irls_it": itn, "active_pairs": int(act.sum()),
-                                   "bytes": 96.0 * float(nv[act, st].sum()), "pass1_ms": round(float(l1[j]), 4), "pass2_ms": round(float(l2[j]), 4)})
+        for j in range(n_sched):
+            st, itn = steps_fine[j // p.max_iter_irls], j % p.max_iter_irls + 1
+            act = it[:, st] >= itn
+            rec = {"outer": j // p.max_iter_irls, "irls_it": itn, "active_pairs": int(act.sum()), "bytes": 96.0 * float(nv[act, st].sum())}
+            if timed:
+                rec.update(pass1_ms=round(float(l1[j]), 4), pass2_ms=round(float(l2[j]), 4))
+            per_launch.append(rec)
         work = [x for x in per_launch if x["bytes"] > 0]
-        detail = {}
-        if work:
+        detail = {"iterations_with_work_per_step": len(work), "iterations_with_work": work}
+        if timed and work:
             full = max(work, key=lambda x: x["bytes"])
             fa = gbs(full["bytes"], full["pass1_ms"] + full["pass2_ms"])
-            detail = {"iterations_with_work_per_step": len(work), "empty_iterations_per_step": len(per_launch) - len(work),
-                      "empty_iterations_ms_per_step": round(sum(x["pass1_ms"] + x["pass2_ms"] for x in per_launch if x["bytes"] == 0), 4),
-                      "fullest_iteration": {**full, "achieved": round(fa, 1), "frac": round(fa / peak, 4)},
-                      "iterations_with_work": work}
-        main_k = kernels["irls_iteration_finest (irls_pass1_kernel + irls_pass2_kernel, all scheduled launches)"]
+            detail.update({"empty_iterations_per_step": len(per_launch) - len(work),
+                           "empty_iterations_ms_per_step": round(sum(x["pass1_ms"] + x["pass2_ms"] for x in per_launch if x["bytes"] == 0), 4),
+                           "fullest_iteration": {**full, "achieved": round(fa, 1), "frac": round(fa / peak, 4)}})
+        main_k = kernels[irls_name]
         traffic, traffic_detail = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this build
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -610,10 +618,13 @@ def main():
                 traffic_detail = tj
         except (OSError, KeyError, ValueError):
             pass
-        roof = {"bound": "hbm", "kernel": "one IRLS iteration at the finest level = irls_pass1_kernel + irls_pass2_kernel (SURVEY 8d: 96 B per valid pixel)",
+        roof = {"bound": "hbm", "kernel": ("irls_loop_kernel at the finest level: every IRLS iteration (pass 1 + pass 2) of every pair of a step in one launch "
+                                            "(SURVEY 8d: 96 B per valid pixel per iteration)") if loop_mode else
+                                           "one IRLS iteration at the finest level = irls_pass1_kernel + irls_pass2_kernel (SURVEY 8d: 96 B per valid pixel)",
                 "achieved": main_k["achieved"], "peak": peak, "unit": "GB/s", "frac": main_k["frac"],
-                "timing": "CUDA events around every launch of the two kernels on the library's stream (the same K steps re-run with plain launches on "
-                          "one stream); achieved = algorithmic bytes of all finest-level iterations / event time of ALL scheduled launches, empty ones included",
+                "timing": "CUDA events around every launch of the kernel on the library's stream (external event nodes of the replayed graph, one stream: "
+                          "the same K steps re-run with profiling on); achieved = algorithmic bytes of all finest-level iterations of a step / event time of "
+                          "ALL launches of the kernel in the step, including those that find no pair to iterate",
                 "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src, **detail,
                 "kernels": kernels,
                 "whole_step": {"algorithmic_bytes_per_step": alg["total"], "ms_per_step": ms_step, "achieved": round(gbs(alg["total"], ms_step), 1),

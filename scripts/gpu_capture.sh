@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run on the GPU box: tests, both bench arms, launch lists, ncu captures of the main kernels.  TAG=r1_q scripts/gpu_capture.sh
 # The ncu --set full captures run the schedule on ONE stream (SF_LANES=1), so launch indices are fixed: one config-2 solve
-# (3 levels x 3 outer steps) has 9 linearise / pose_update, 8 warp, 6 irls_fused (levels 2 and 1) and 18 x (pass1, pass2)
+# (3 levels x 3 outer steps) has 9 linearise / pose_update, 8 warp, 6 irls_fused (levels 2 and 1) and 3 irls_loop (level 0)
 # launches; profile_step.py does two solves and the skips below select a finest-level instance of the second (warm) one.
 TAG=${TAG:-r1_x}
 PAIRS=${PAIRS:-512}
@@ -17,8 +17,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/profile_step.py $PAIRS 2 > gpurun_out/${TAG}_ls.log 2>&1
 tail -1 gpurun_out/${TAG}_ls.log
 export SF_LANES=1
-for k in ${KERNELS:-irls_pass1_kernel irls_pass2_kernel linearise_kernel kmeans_kernel warp_kernel warp_normalise_kernel irls_fused_kernel label_connect_kernel}; do
+for k in ${KERNELS:-irls_loop_kernel linearise_kernel kmeans_kernel warp_kernel warp_normalise_kernel irls_fused_kernel label_connect_kernel}; do
   case $k in
+    irls_loop_kernel) SKIP=${SKIP_LOOP:-3};;
     irls_pass1_kernel|irls_pass2_kernel) SKIP=${SKIP_PASS:-18};;
     linearise_kernel|pose_update_kernel) SKIP=${SKIP_LIN:-15};;
     warp_kernel|warp_normalise_kernel) SKIP=${SKIP_WARP:-13};;

@@ -33,7 +33,13 @@ def read(rep):
     return out
 
 
+try:
+    stats = json.load(open(os.path.join(ROOT, "gpurun_out", "profile_step_stats.json")))
+except OSError:
+    stats = {}
 alg = {
+    "irls_loop_kernel": (stats.get("irls_loop_finest_outer0_bytes"), "96 B per valid pixel per IRLS iteration run, every pair's whole loop of the first finest-level step "
+                                                                     f"({stats.get('irls_iterations_mean', 0):.2f} iterations per pair on average)"),
     "irls_pass1_kernel": (48.0 * N0 * pairs, "48 B per valid pixel, first iteration of the first finest-level step (all pairs iterate)"),
     "irls_pass2_kernel": (48.0 * N0 * pairs, "48 B per valid pixel, same iteration"),
     "linearise_kernel": (61.0 * P0 * pairs, "61 B per level-0 pixel"),
@@ -54,7 +60,12 @@ for k, (a, note) in alg.items():
     d = m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]
     out["kernels"][k] = {"dram_bytes": d, "algorithmic_bytes": a, "dram_over_algorithmic": (d / a if a else None), "us_under_ncu": m["us_under_ncu"], "note": note}
 k = out["kernels"]
-if "irls_pass1_kernel" in k and "irls_pass2_kernel" in k:
+if "irls_loop_kernel" in k and k["irls_loop_kernel"]["algorithmic_bytes"]:
+    e = k["irls_loop_kernel"]
+    out["irls_iteration_finest"] = {"dram_bytes": e["dram_bytes"], "algorithmic_bytes": e["algorithmic_bytes"], "dram_over_algorithmic": e["dram_over_algorithmic"],
+                                    "note": "one launch of irls_loop_kernel = all IRLS iterations of the first finest-level step: the stored-row format moves 57 B per LEVEL "
+                                            "pixel per pass for 48 B per VALID pixel"}
+elif "irls_pass1_kernel" in k and "irls_pass2_kernel" in k:
     d = k["irls_pass1_kernel"]["dram_bytes"] + k["irls_pass2_kernel"]["dram_bytes"]
     a = 96.0 * N0 * pairs
     out["irls_iteration_finest"] = {"dram_bytes": d, "algorithmic_bytes": a, "dram_over_algorithmic": d / a,

@@ -26,6 +26,14 @@ def main():
         s.launch()
         s.sync()
     print("launches per solve:", s.last_launch_count)
+    # algorithmic bytes of the launches the ncu captures pick (first finest-level step: every pair's IRLS loop at level 0)
+    import json
+    nv, it = s.step_stats()
+    st = (levels - 1) * s.params.max_iter_per_level
+    out = {"pairs": batch, "config": config, "irls_loop_finest_outer0_bytes": 96.0 * float((nv[:, st].astype(np.float64) * it[:, st]).sum()),
+           "valid_pixels_mean": float(nv[:, st].mean()), "irls_iterations_mean": float(it[:, st].mean())}
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/profile_step_stats.json", "w"))
 
 
 if __name__ == "__main__":

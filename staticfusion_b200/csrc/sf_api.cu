@@ -63,6 +63,7 @@ struct sf_ctx {
     struct GraphRec { int n_pairs, n_frames, stop_step, pyramids, history, lanes, prof; cudaGraphExec_t exec; int launches; std::vector<ProfRec> prof_recs; };
     std::vector<GraphRec> graphs;
     bool use_graph = true;
+    bool irls_loop = true;      // SF_IRLS_LOOP=0: one launch per pass and iteration instead of the queue-driven loop kernel (A-B measurements)
     int fused_max_tiles = 300;  // levels with at most this many 64-pixel tiles per pair run the fused IRLS kernel (SF_FUSED_MAX_TILES)
     // depth pre-filter scratch (grown on demand)
     uint16_t* d_raw = nullptr;
@@ -75,7 +76,8 @@ struct sf_ctx {
     static constexpr int MAX_LANES = 4;
     cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
-    int* d_lane_gcount = nullptr;    // [MAX_LANES][4]
+    int* d_lane_gcount = nullptr;    // [MAX_LANES][GCOUNT_CELLS]
+    unsigned long long* d_irls_q = nullptr;  // [MAX_LANES][q_cap]
     int* d_iter_list = nullptr;      // [2][max_batch]
     int* d_lane_work_ctr = nullptr;  // [MAX_LANES][MAX_WORK_CTRS]
     int lanes_override = 0, last_lanes = 1;
@@ -232,7 +234,8 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     if (!c) return fail(SF_E_NOMEM, "host allocation failed");
     c->p = *p; c->device = device; c->max_batch = max_batch; c->flags = flags; c->levels = p->ctf_levels;
     if (const char* e = std::getenv("SF_FUSED_MAX_TILES")) c->fused_max_tiles = std::atoi(e);  // tuning / A-B measurements
-    c->fused_max_tiles = std::min(c->fused_max_tiles, 4 * MAX_TILES_PER_WARP_ITEM);  // the fused kernel's smallest block has 4 warps
+    c->fused_max_tiles = std::min(c->fused_max_tiles, 4 * MAX_TILES_PER_WARP_ITEM);
+    if (const char* e = std::getenv("SF_IRLS_LOOP")) c->irls_loop = std::atoi(e) != 0;  // the fused kernel's smallest block has 4 warps
     fill_dev_params(c);
     const size_t off = fill_geometry(c);
     Arena& a = c->a;
@@ -271,7 +274,9 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     ok = ok && alloc((void**)&a.tiles, tiles_per_pair(a.P0) * TILE_BYTES * F);
     ok = ok && alloc((void**)&a.active_list, sizeof(int) * F);
     ok = ok && alloc((void**)&c->d_iter_list, sizeof(int) * 2 * F);
-    ok = ok && alloc((void**)&c->d_lane_gcount, sizeof(int) * 4 * sf_ctx::MAX_LANES);
+    ok = ok && alloc((void**)&c->d_lane_gcount, sizeof(int) * GCOUNT_CELLS * sf_ctx::MAX_LANES);
+    a.q_cap = (int)irls_queue_capacity(F, p->max_iter_irls, a.P0);
+    ok = ok && alloc((void**)&c->d_irls_q, sizeof(unsigned long long) * (size_t)a.q_cap * sf_ctx::MAX_LANES);
     ok = ok && alloc((void**)&c->d_lane_work_ctr, sizeof(int) * MAX_WORK_CTRS * sf_ctx::MAX_LANES);
     if (ok && (flags & 1)) ok = alloc((void**)&a.dbg, sizeof(float) * NPLANES * a.P0 * F);
     ok = ok && alloc((void**)&a.ctl, sizeof(PairCtl) * F);
@@ -289,7 +294,7 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
         return fail(SF_E_NOMEM, msg);
     }
     a.cur_idx = c->d_cur_idx; a.pred_idx = c->d_pred_idx;
-    a.gcount = c->d_lane_gcount; a.work_ctr = c->d_lane_work_ctr;  // lane 0's slices
+    a.gcount = c->d_lane_gcount; a.work_ctr = c->d_lane_work_ctr; a.irls_q = c->d_irls_q;  // lane 0's slices
     a.iter_list0 = c->d_iter_list; a.iter_list1 = c->d_iter_list + F;
     if (const char* e = std::getenv("SF_LANES")) c->lanes_override = std::atoi(e);
     c->lane_stream[0] = c->stream;
@@ -320,7 +325,8 @@ int sf_create(sf_ctx** out, const sf_params* p, int device, int max_batch, int f
     cudaMemsetAsync(a.acc_d, 0, sizeof(long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.acc_iw, 0, sizeof(unsigned long long) * a.P0 * F, c->stream);
     cudaMemsetAsync(a.tiles, 0xff, tiles_per_pair(a.P0) * TILE_BYTES * F, c->stream);  // every label byte = invalid
-    cudaMemsetAsync(c->d_lane_gcount, 0, sizeof(int) * 4 * sf_ctx::MAX_LANES, c->stream);
+    cudaMemsetAsync(c->d_lane_gcount, 0, sizeof(int) * GCOUNT_CELLS * sf_ctx::MAX_LANES, c->stream);
+    cudaMemsetAsync(c->d_irls_q, 0, sizeof(unsigned long long) * (size_t)a.q_cap * sf_ctx::MAX_LANES, c->stream);  // generation 0 = never valid
     cudaMemsetAsync(a.pcar, 0xff, sizeof(float) * NC * F, c->stream);  // all-ones = quiet NaN (FrontEnd.cpp:105)
     cudaMemsetAsync(a.ring_d, 0, sizeof(float) * a.P0 * 5, c->stream);
     cudaMemsetAsync(a.ring_i, 0, sizeof(float) * a.P0 * 5, c->stream);
@@ -345,7 +351,7 @@ void sf_destroy(sf_ctx* c) {
     cudaFree(a.ctl); cudaFree(a.out); cudaFree(a.b_perpixel); cudaFree(a.pcar); cudaFree(a.ring_d); cudaFree(a.ring_i); cudaFree(a.ring_T);
     cudaFree(a.trace); cudaFree(a.stepstat); cudaFree(c->d_raw); cudaFree(c->d_filt); cudaFree(c->d_cvt);
     drop_graphs(c);
-    cudaFree(c->d_lane_gcount); cudaFree(c->d_lane_work_ctr); cudaFree(c->d_iter_list);
+    cudaFree(c->d_lane_gcount); cudaFree(c->d_lane_work_ctr); cudaFree(c->d_iter_list); cudaFree(c->d_irls_q);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_pcar) cudaFreeHost(c->h_pcar);
     for (int l = 1; l < sf_ctx::MAX_LANES; l++) { if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
@@ -453,7 +459,8 @@ static Arena lane_arena(const sf_ctx* c, int lane, int lo) {
     a.tiles += o * tiles_per_pair(a.P0) * TILE_BYTES;
     if (a.dbg) a.dbg += o * NPLANES * a.P0;
     a.active_list += o; a.iter_list0 += o; a.iter_list1 += o;
-    a.gcount = c->d_lane_gcount + 4 * lane;
+    a.gcount = c->d_lane_gcount + GCOUNT_CELLS * lane;
+    a.irls_q = c->d_irls_q + (size_t)a.q_cap * lane;
     a.work_ctr = c->d_lane_work_ctr + (size_t)MAX_WORK_CTRS * lane;
     a.ctl += o; a.out += o;
     a.b_perpixel += o * a.P0;
@@ -465,7 +472,10 @@ static Arena lane_arena(const sf_ctx* c, int lane, int lo) {
 
 static int choose_lanes(const sf_ctx* c) {
     if (c->prof_on) return 1;  // per-kernel events time each kernel alone on one stream
-    int n = c->lanes_override > 0 ? c->lanes_override : (c->n_pairs >= 384 ? 3 : c->n_pairs >= 192 ? 2 : 1);
+    // With the queue-driven IRLS loop kernel a lane's kernels are self-contained (no trail of tail launches to overlap): one
+    // lane with full-size launches is fastest and callers overlap whole batches on several contexts instead (measured, 512
+    // QVGA pairs, 2 contexts: 1 / 2 / 3 / 4 lanes = 5.10 / 5.23 / 5.35 / 5.71 ms per step).  The per-launch passes keep the old rule.
+    int n = c->lanes_override > 0 ? c->lanes_override : (c->irls_loop ? 1 : (c->n_pairs >= 384 ? 3 : c->n_pairs >= 192 ? 2 : 1));
     if (n > sf_ctx::MAX_LANES) n = sf_ctx::MAX_LANES;
     if (n > c->n_pairs) n = c->n_pairs;
     return n < 1 ? 1 : n;
@@ -492,6 +502,9 @@ static bool enqueue_lane(sf_ctx* c, const Arena& a, cudaStream_t stream, int lo,
             if ((int)tiles_per_pair((size_t)g.P) <= c->fused_max_tiles) {  // small level: one block runs the pair's whole IRLS loop
                 ProfScope ps(c, 5, image_level);
                 n += launch_irls_fused(a, dp, g, i, k, cfg);
+            } else if (c->irls_loop) {  // large level: ONE launch runs the IRLS loops of all pairs through a device-side item queue
+                ProfScope ps(c, 5, image_level);
+                n += launch_irls_loop(a, dp, g, i, k, cfg);
             } else
                 for (int it = 1; it <= c->p.max_iter_irls; it++) {
                     { ProfScope ps(c, 5, image_level); n += launch_irls_pass1(a, dp, g, i, k, it, cfg); }

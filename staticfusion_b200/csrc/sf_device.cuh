@@ -128,6 +128,7 @@ struct PairCtl {
     int it_done;       // IRLS iterations done in the current step
     int status, total_irls;
     int km_iters;      // Lloyd iterations of the last kMeans3DCoord (KMeans.cpp:167-228)
+    int items_cur;     // items the pair's current IRLS pass was cut into (irls_loop_kernel: ticket target)
     unsigned ticket1, ticket2;
     // ---- 5-frame history (computeResidualsAgainstPreviousImage, FrontEnd.cpp:896-1069) ----
     float Thist[12];          // rows 0..2 of (prod odomBuffer * T_odometry)^-1

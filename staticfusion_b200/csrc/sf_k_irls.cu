@@ -513,6 +513,233 @@ irls_pass2_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer,
     }
 }
 
+// ---- queue-driven IRLS loop: ONE launch runs the IRLS loops of all pairs of a large level ----------------------------
+// The static schedule used to enqueue max_iter_irls x (pass 1, pass 2) launches per step; after the second iteration most of
+// them found no pair (the drivers' threshold ends the loop after 2-3 iterations for ~95 % of the pairs) and every launch
+// boundary made the pairs that were still iterating wait for each other.  Here persistent blocks pop WORK ITEMS
+// (pair, pass, tile range) from a queue in global memory; the block that finishes the last item of a pair's pass runs that
+// pass's tail (6x6 solve / 24x24 segmentation solve + exit test) and pushes the items of the pair's next pass, or retires the
+// pair.  Pairs advance through their iterations independently; there is no grid-wide barrier and no wait other than for a
+// queue slot to be filled, and a slot a block waits for is always filled by a block that is running (a pair cannot retire
+// while one of its items is unprocessed), so the loop cannot deadlock whatever the number of resident blocks.
+// A slot is valid when it carries the step's generation (Arena::gcount[4], bumped by step_begin_kernel): no reset pass.
+// Per-pair state written by one block and read by another goes through L2: every block executes a device-scope fence after
+// it pops an item (which also drops the SM's L1 lines) before it touches the pair.
+constexpr int LOOP_BLOCKS_PER_PAIR = 2;  // measured 2 / 4 / 8 / 16 / 64: 5.35 / 5.38 / 5.37 / 5.40 / 5.43 ms per step (3 lanes), flat with one lane
+__device__ __forceinline__ unsigned long long q_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int vol_load(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// items a pass of one pair is cut into, from the number of pairs still iterating (same rule as pass_items)
+__device__ __forceinline__ int loop_items_per_pair(int n_iterating, int level_tiles, int resident_blocks) {
+    int want = n_iterating > 0 ? (4 * resident_blocks + n_iterating - 1) / n_iterating : 1;
+    const int most = level_tiles / (4 * PS_WARPS) > 1 ? level_tiles / (4 * PS_WARPS) : 1;
+    if (want > most) want = most;
+    if (want < 1) want = 1;
+    const int need = (level_tiles + MAX_TILES_PER_WARP_ITEM * PS_WARPS - 1) / (MAX_TILES_PER_WARP_ITEM * PS_WARPS);
+    if (want < need) want = need;
+    const int per = (level_tiles + want - 1) / want;
+    return (level_tiles + per - 1) / per;
+}
+// one thread: publish the items of `pass` (0 = pass 1, 1 = pass 2) of a pair.  The pair's state was written before.
+__device__ __forceinline__ void loop_push(const Arena& a, PairCtl& c, int pair, int pass, int level_tiles, int resident_blocks, unsigned gen) {
+    const int K = loop_items_per_pair(vol_load(&a.gcount[1]), level_tiles, resident_blocks);
+    c.items_cur = K;
+    __threadfence();  // state (and items_cur) before the items
+    const int base = atomicAdd(&a.gcount[6], K);
+    for (int j = 0; j < K; j++)
+        if (base + j < a.q_cap)
+            atomicExch(&a.irls_q[base + j], ((unsigned long long)gen << 32) | ((unsigned long long)pair << 12) | ((unsigned long long)pass << 11) | (unsigned long long)j);
+}
+
+__global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM)
+irls_loop_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer, int resident_blocks, int pattern, int blocks_per_pair) {
+    if (a.gcount[1] == 0) return;  // no pair enters the loop in this step (written by step_prep_kernel, an earlier launch)
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float s_b[NC];
+    __shared__ float s_var[6];
+    __shared__ float s_mc[7], s_md[7];
+    __shared__ long long s_part[PS_WARPS][28];
+    __shared__ long long s_fix[PS_WARPS][NC];
+    __shared__ int s_cnt[PS_WARPS][NC];
+    __shared__ long long s_rs[PS_WARPS];
+    __shared__ double s_A[NC * 25];
+    __shared__ double s_rhs[NC], s_x[NC];
+    __shared__ unsigned char s_zero[NC];
+    __shared__ float s_aver_label[NC];
+    __shared__ int s_last;
+    __shared__ long long s_item;
+    const PassRing pr = pass_ring_setup(dyn_smem, warp, lane, tid);
+    TileStream ts;
+    ts.ring = pr.ring; ts.bars = pr.bars; ts.phase = 0;
+    const int level_tiles = (int)tiles_per_pair((size_t)g.P);
+    const unsigned gen = (unsigned)a.gcount[4];
+    if (tid == 0) atomicAdd(&a.gcount[7], 1);  // blocks alive in this loop
+    if (blockIdx.x == 0) {  // the pairs step_prep_kernel listed enter the loop: items of their first pass 1
+        const int n = a.gcount[2];
+        for (int s = tid; s < n; s += PS_THREADS) {
+            const int pair = a.iter_list0[s];
+            loop_push(a, a.ctl[pair], pair, 0, level_tiles, resident_blocks, gen);
+        }
+    }
+    for (;;) {
+        // ---- pop: claim the head slot once it carries this step's generation.  A block that finds nothing to do leaves when
+        // every pair has retired, or when more blocks are alive than the pairs still iterating can keep busy (LOOP_BLOCKS_PER_PAIR
+        // each): an idle block would only keep its SM from the kernels of the other lanes.
+        __syncthreads();  // the previous item's shared state is no longer read
+        if (tid == 0) {
+            long long got = -1;
+            for (long long spin = 0; spin < (1ll << 24) && got == -1; spin++) {
+                if (vol_load(&a.gcount[6]) > vol_load(&a.gcount[5])) {  // items are waiting: take a ticket, then its slot
+                    const int idx = atomicAdd(&a.gcount[5], 1);
+                    if (idx >= a.q_cap) break;
+                    for (long long w = 0; w < (1ll << 24); w++) {  // (another block may have taken the last one: then this slot is filled by the next push)
+                        const unsigned long long v = q_load(&a.irls_q[idx]);
+                        if ((unsigned)(v >> 32) == gen) { got = (long long)(v & 0xffffffffull); break; }
+                        if (vol_load(&a.gcount[1]) == 0) { got = -3; break; }
+                        __nanosleep(64);
+                    }
+                    if (got == -1) got = -3;
+                    break;
+                }
+                const int rem = vol_load(&a.gcount[1]);
+                if (rem == 0) { got = -3; break; }  // every pair has retired: nothing will be pushed any more
+                const int live = vol_load(&a.gcount[7]);
+                if (live > blocks_per_pair * rem) {
+                    if (atomicCAS(&a.gcount[7], live, live - 1) == live) got = -2;
+                    continue;
+                }
+                __nanosleep(200);
+            }
+            if (got != -2 && got < 0) atomicSub(&a.gcount[7], 1);
+            s_item = got;
+        }
+        __syncthreads();
+        const long long item = s_item;
+        if (item < 0) break;
+        __threadfence();  // acquire: the pusher's state is visible, stale L1 lines are dropped
+        const int pair = (int)(item >> 12), pass = (int)((item >> 11) & 1), chunk = (int)(item & 2047);
+        PairCtl& c = a.ctl[pair];
+        const int K = c.items_cur;
+        const int tiles_per_item = (level_tiles + K - 1) / K;
+        const int t0 = chunk * tiles_per_item, t1 = min(t0 + tiles_per_item, level_tiles);
+        const int it = c.it_done + 1;
+        ts.begin(a.tiles + (size_t)pair * tiles_per_pair(a.P0) * TILE_BYTES, t0, t1, pattern, warp, lane);  // copies fly while the constants load
+        const float inv_max_c = c.inv_max_c, inv_max_d = c.inv_max_d;
+        if (pass == 0) {
+            // ---------------- pass 1: robust weights (:615-637), normal equations (:640-641)
+            if (tid < NC) s_b[tid] = fmaxf(0.f, fminf(1.f, c.b_segm[tid]));  // :624
+            if (tid < 6) s_var[tid] = c.var[tid];
+            if (tid < 7) { s_mc[tid] = c.mcs[tid]; s_md[tid] = c.mds[tid]; }
+            const float inv_c_Cauchy = 1.f / (prm.kc_cauchy * c.aver_res);  // :615
+            __syncthreads();
+            double acc[27];
+#pragma unroll
+            for (int i = 0; i < 27; i++) acc[i] = QMAGIC_D;
+            for (int i = 0; i < ts.count; i++) {
+                const unsigned char* tile = ts.wait(i);
+                pass1_tile(tile, lane, it, inv_max_c, inv_max_d, inv_c_Cauchy, s_b, s_var, s_mc, s_md, acc);
+                ts.release(i, lane);
+            }
+            long long mine = 0;
+#pragma unroll
+            for (int i = 0; i < 27; i++) {
+                const long long ws = warp_sum_i64_exact(fixacc_value(acc[i]));
+                if (lane == i) mine = ws;
+            }
+            if (lane < 27) s_part[warp][lane] = mine;
+            __syncthreads();
+            if (tid < 27) {
+                long long t = 0;
+#pragma unroll
+                for (int w = 0; w < PS_WARPS; w++) t += s_part[w][tid];
+                if (t) atomic_add_ll(&c.acc_ne[tid], t);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned t = atomicAdd(&c.ticket1, 1u);
+                s_last = (t == (unsigned)K - 1u) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_last) continue;
+            __threadfence();
+            if (tid == 0) {  // tail: 6x6 solve in double (:642), then the pair's pass 2 enters the queue
+                long long ne[27];
+                for (int i = 0; i < 27; i++) ne[i] = __ldcg(&c.acc_ne[i]);
+                irls_solve6(c, ne);
+                for (int i = 0; i < 27; i++) c.acc_ne[i] = 0;
+                c.ticket1 = 0;
+                loop_push(a, c, pair, 1, level_tiles, resident_blocks, gen);
+            }
+        } else {
+            // ---------------- pass 2: residuals of the new solution (:644-646), per-label sums (:650-667)
+            for (int q = tid; q < PS_WARPS * NC; q += PS_THREADS) { (&s_fix[0][0])[q] = 0; (&s_cnt[0][0])[q] = 0; }
+            if (tid < 6) s_var[tid] = c.var[tid];
+            const int rexp = c.rexp;
+            const float rscale = ldexpf(1.f, rexp), lscale = ldexpf(1.f, rexp + (LABEL_BITS - QSCALE_BITS - 1));
+            __syncthreads();
+            float var[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) var[i] = s_var[i];
+            double rs = QMAGIC_D;
+            for (int i = 0; i < ts.count; i++) {
+                const unsigned char* tile = ts.wait(i);
+                pass2_tile(tile, lane, inv_max_c, inv_max_d, var, rscale, lscale, s_fix[warp], s_cnt[warp], rs);
+                ts.release(i, lane);
+            }
+            const long long wrs = warp_sum_i64_exact(fixacc_value(rs));
+            if (lane == 0) s_rs[warp] = wrs;
+            __syncthreads();
+            if (tid < NC) {
+                long long f = 0;
+                int n = 0;
+#pragma unroll
+                for (int w = 0; w < PS_WARPS; w++) { f += s_fix[w][tid]; n += s_cnt[w][tid]; }
+                if (n) { atomic_add_ll(&c.lab_fix[tid], f); atomicAdd(&c.lab_cnt[tid], n); }
+            }
+            if (tid == 0) {
+                long long t = 0;
+                for (int w = 0; w < PS_WARPS; w++) t += s_rs[w];
+                if (t) atomic_add_ll(&c.acc_rs, t);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned t = atomicAdd(&c.ticket2, 1u);
+                s_last = (t == (unsigned)K - 1u) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_last) continue;
+            __threadfence();
+            if (warp == 0) {  // tail, one warp: segmentation solve (SegmentationBackground.cpp:133-174), exit test (:676-683)
+                long long lf = 0;
+                int lc = 0;
+                if (lane < NC) { lf = __ldcg(&c.lab_fix[lane]); lc = __ldcg(&c.lab_cnt[lane]); }
+                const long long rs_total = __ldcg(&c.acc_rs);
+                const bool done = irls_seg_tail(c, prm, lf, lc, rs_total, var, it, s_A, s_rhs, s_x, s_zero, s_aver_label, lane,
+                                                irls_trace_rec(a, prm, pair, level_i, k_outer, it));
+                if (lane < NC) { c.lab_fix[lane] = 0; c.lab_cnt[lane] = 0; }
+                __threadfence();  // every lane's part of the pair's state (b_segm, cleared cells) is out before lane 0 publishes
+                __syncwarp();
+                if (lane == 0) {
+                    c.acc_rs = 0;
+                    c.ticket2 = 0;
+                    if (done) { __threadfence(); atomicSub(&a.gcount[1], 1); }  // the pair retires: its state is complete before the count drops
+                    else loop_push(a, c, pair, 0, level_tiles, resident_blocks, gen);
+                }
+            }
+        }
+    }
+}
+
 // ---- fused IRLS loop: ONE block runs all iterations of a pair (both passes, both solves, the exit test) with the
 // per-pair state in shared memory.  Used for the levels whose per-pair data is small: there the multi-block passes
 // are bound by launch / ticket / tail latency (12 launches per step), not by bandwidth.  Same per-tile bodies and
@@ -799,6 +1026,7 @@ void prepare_kernels() { extern void pass_kernel_attrs_impl(); pass_kernel_attrs
 void pass_kernel_attrs_impl() {  // per device (function attributes are not shared between devices): called by every sf_create
     cudaFuncSetAttribute(irls_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM);
     cudaFuncSetAttribute(irls_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM);
+    cudaFuncSetAttribute(irls_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM);
     cudaFuncSetAttribute(irls_fused_kernel<PS_WARPS, PS_BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem(PS_WARPS));
     cudaFuncSetAttribute(irls_fused_kernel<FW_SMALL, FB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem(FW_SMALL));
 }
@@ -815,6 +1043,22 @@ static inline int pass_grid(const Arena& a, int P, int n_pairs) {
 int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, int, int, int it, const LaunchCfg& c) {
     const int slot = (*c.next_ctr)++ % MAX_WORK_CTRS;
     irls_pass1_kernel<<<pass_grid(a, g.P, c.n_pairs), PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, it, a.num_sms * PS_BLOCKS_PER_SM, tile_pattern(g.cols), slot);
+    return 1;
+}
+
+// items one IRLS loop of a lane can push: every pass of every iteration of every pair, cut as finely as loop_items_per_pair allows
+size_t irls_queue_capacity(int max_pairs, int max_iter_irls, size_t P0) {
+    const size_t tiles = tiles_per_pair(P0);
+    const size_t most = tiles / (4 * PS_WARPS) > 1 ? tiles / (4 * PS_WARPS) : 1;
+    const size_t need = (tiles + (size_t)MAX_TILES_PER_WARP_ITEM * PS_WARPS - 1) / ((size_t)MAX_TILES_PER_WARP_ITEM * PS_WARPS);
+    return (size_t)max_pairs * (size_t)max_iter_irls * 2 * ((most > need ? most : need) + 1) + 64;
+}
+
+// whole IRLS loop of a step for a large level: persistent blocks, device-side item queue
+int launch_irls_loop(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, const LaunchCfg& c) {
+    const int resident = a.num_sms * PS_BLOCKS_PER_SM;
+    static const int bpp = std::getenv("SF_LOOP_BPP") ? std::atoi(std::getenv("SF_LOOP_BPP")) : LOOP_BLOCKS_PER_PAIR;  // A-B measurements
+    irls_loop_kernel<<<pass_grid(a, g.P, c.n_pairs), PS_THREADS, PS_DYN_SMEM, c.stream>>>(a, p, g, level_i, k, resident, tile_pattern(g.cols), bpp);
     return 1;
 }
 

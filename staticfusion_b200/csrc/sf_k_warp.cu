@@ -19,7 +19,10 @@ namespace sf {
 constexpr int SB_THREADS = 1024;
 __global__ void __launch_bounds__(SB_THREADS) step_begin_kernel(Arena a, int level_i, int n_pairs) {
     __shared__ int s_count;
-    if (threadIdx.x == 0) { s_count = 0; a.gcount[1] = 0; a.gcount[2] = 0; a.gcount[3] = 0; }
+    if (threadIdx.x == 0) {
+        s_count = 0; a.gcount[1] = 0; a.gcount[2] = 0; a.gcount[3] = 0;
+        a.gcount[4] += 1; a.gcount[5] = 0; a.gcount[6] = 0; a.gcount[7] = 0;  // IRLS item queue of this step: new generation, empty, no block alive
+    }
     __syncthreads();
     for (int pair = threadIdx.x; pair < n_pairs; pair += SB_THREADS) {
         PairCtl& c = a.ctl[pair];

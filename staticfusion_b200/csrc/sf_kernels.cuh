@@ -31,7 +31,10 @@ struct Arena {
     float* warp_i;              // [F][P0]
     uint8_t* tiles;             // [F][tiles_per_pair(P0)][TILE_BYTES] raw Jacobian rows + valid-pixel labels
     float* dbg;                 // [F][NPLANES][P0] linearisation planes, only with the trace flag (else nullptr)
-    int* gcount;                // [4]: pairs active in the current step, pairs still inside the IRLS loop, lengths of iter_list0 / iter_list1
+    int* gcount;                // [GCOUNT_CELLS]: [0] pairs active in the current step, [1] pairs still inside the IRLS loop, [2] / [3] lengths of
+                                // iter_list0 / iter_list1, [4] generation of the IRLS item queue (one per step), [5] / [6] its head / tail, [7] blocks alive in the loop kernel
+    unsigned long long* irls_q; // [q_cap] item queue of irls_loop_kernel: (generation << 32) | (pair << 12) | (pass << 11) | chunk
+    int q_cap;
     int* iter_list0;            // [F] pairs that run IRLS iteration it (odd it); pass 2 of iteration it appends the pairs that go on
     int* iter_list1;            // [F] ... to the other list (even it), so every pass launch is sized by the pairs still iterating
     int* active_list;           // [F] indices of the pairs active in the current step (first gcount[0] entries)
@@ -52,6 +55,7 @@ struct Arena {
 };
 
 constexpr int MAX_WORK_CTRS = 4096;
+constexpr int GCOUNT_CELLS = 8;
 
 struct LaunchCfg {
     cudaStream_t stream;
@@ -74,6 +78,8 @@ int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, con
 int launch_irls_pass1(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
 int launch_irls_pass2(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, int it, const LaunchCfg& c);
 int launch_irls_fused(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, const LaunchCfg& c);
+int launch_irls_loop(const Arena& a, const DevParams& p, const LevelGeom& g, int level_i, int k, const LaunchCfg& c);
+size_t irls_queue_capacity(int max_pairs, int max_iter_irls, size_t P0);  // items one IRLS loop of a lane can push
 int launch_pose_update(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c);
 int launch_finish(const Arena& a, const DevParams& p, const LevelGeom& g0, const LaunchCfg& c);
 // computeResidualsAgainstPreviousImage (FrontEnd.cpp:896-1069).  mode 0: pairs of a sequence, pair p >= 4 warps frame

@@ -99,10 +99,10 @@ def test_config2_three_levels_against_the_oracle(gpu, oracle_mod):
     s.close()
 
 
-def test_bench_shaped_batch_512_pairs_three_lanes(gpu, oracle_mod):
-    """The exact batch bench.py times (config 2: 512 pairs cycled through 65 rendered frames, three lanes with per-iteration
-    work lists, CUDA-graph replay): 48 pairs sampled across the lanes against the oracle, bit for bit, on the first launch and
-    on the replay."""
+def test_bench_shaped_batch_512_pairs(gpu, oracle_mod, monkeypatch):
+    """The exact batch bench.py times (config 2: 512 pairs cycled through 65 rendered frames, the queue-driven IRLS loop kernel,
+    CUDA-graph replay): 48 sampled pairs against the oracle, bit for bit, on the first launch and on the replay; the same batch
+    cut into three lanes and with the per-launch IRLS passes (SF_IRLS_LOOP=0) gives the same bits."""
     import bench
     rows, cols, F, nd = 240, 320, 512, 65
     d, c = bench.make_frames("dynamic", nd, rows, cols)
@@ -110,12 +110,23 @@ def test_bench_shaped_batch_512_pairs_three_lanes(gpu, oracle_mod):
     p = gpu.default_params(rows, cols, ctf_levels=3)
     s = gpu.StaticFusionSolver(p, max_batch=F)
     r1 = s.solve_sequence(d[seq], c[seq])
-    assert s.lanes == 3
+    assert s.lanes == 1
     r = s.solve_sequence(d[seq], c[seq])  # graph replay
     for name in ("T", "b_perpixel", "labels", "irls_iters", "status", "b_segm"):
         assert np.array_equal(getattr(r1, name), getattr(r, name)), name
+    for env in ({"SF_LANES": "3"}, {"SF_IRLS_LOOP": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s2 = gpu.StaticFusionSolver(p, max_batch=F)
+        r2 = s2.solve_sequence(d[seq], c[seq])
+        assert s2.lanes == 3
+        for name in ("T", "b_perpixel", "labels", "irls_iters", "status", "b_segm"):
+            assert np.array_equal(getattr(r2, name), getattr(r, name)), (env, name)
+        s2.close()
+        for k in env:
+            monkeypatch.delenv(k)
     rng = np.random.default_rng(5)
-    ks = sorted(set(rng.choice(F, 40, replace=False).tolist()) | {0, 170, 171, 172, 341, 342, 343, 511})
+    ks = sorted(set(rng.choice(F, 40, replace=False).tolist()) | {0, 170, 171, 172, 341, 342, 343, 511})  # incl. the 3-lane cut points
     ref = oracle_pairs(oracle_mod, oracle_params_from(oracle_mod, p), [(d[seq[k + 1]], c[seq[k + 1]], d[seq[k]], c[seq[k]]) for k in ks])
     Tg = r.T_matrices()
     for k, o in zip(ks, ref):
