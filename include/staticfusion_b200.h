@@ -51,6 +51,7 @@ extern "C" {
 #define SF_STATUS_NO_VALID_PIXELS 1 /* validPixels empty at some step: reference divides by zero (FrontEnd.cpp:505-509) */
 #define SF_STATUS_ZERO_RESIDUAL 2   /* mean |B| == 0 (identical images): reference produces NaN (FrontEnd.cpp:615) */
 #define SF_STATUS_SINGULAR 4        /* a zero pivot was met in the 6x6 normal equations */
+#define SF_STATUS_INTERNAL 16       /* the IRLS loop kernel gave up waiting for work that never came (never expected): results of the batch are invalid */
 
 /* memory space of a pointer argument */
 #define SF_MEM_HOST 0

@@ -606,8 +606,7 @@ irls_loop_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer, 
                         if (vol_load(&a.gcount[1]) == 0) { got = -3; break; }
                         __nanosleep(64);
                     }
-                    if (got == -1) got = -3;
-                    break;
+                    break;  // got == -1: the wait for the ticket's slot ran out
                 }
                 const int rem = vol_load(&a.gcount[1]);
                 if (rem == 0) { got = -3; break; }  // every pair has retired: nothing will be pushed any more
@@ -617,6 +616,11 @@ irls_loop_kernel(Arena a, DevParams prm, LevelGeom g, int level_i, int k_outer, 
                     continue;
                 }
                 __nanosleep(200);
+            }
+            if (got == -1) {  // the bounded wait ran out: must never happen; flag the batch and release the other blocks
+                const int n = a.gcount[2];
+                for (int q = 0; q < n; q++) atomicOr(&a.ctl[a.iter_list0[q]].status, SF_STATUS_INTERNAL);
+                atomicExch(&a.gcount[1], 0);
             }
             if (got != -2 && got < 0) atomicSub(&a.gcount[7], 1);
             s_item = got;
