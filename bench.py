@@ -486,8 +486,8 @@ def main():
     del g_bgr, g_mm
     torch.cuda.empty_cache()
     # pipeline shape (pairs per chunk x contexts) and depth (steps in flight behind the one being enqueued): scripts/exp_e2e.py
-    e2e_chunk, e2e_ctx = (int(v) for v in os.environ.get("SF_BENCH_E2E", "171x6").split("x"))
-    e2e_depth = int(os.environ.get("SF_BENCH_E2E_DEPTH", "2"))
+    e2e_chunk, e2e_ctx = (int(v) for v in os.environ.get("SF_BENCH_E2E", "256x6").split("x"))
+    e2e_depth = int(os.environ.get("SF_BENCH_E2E_DEPTH", "3"))
     e2e_chunk = max(1, min(e2e_chunk, (n_batch + 1) // 2))  # at least two chunks per step, so that a step's copies overlap its own solves
     # N > 1: ONE all-gather per step on every rank (chunk counts differ between ranks of a sharded sequence): every chunk's
     # context stages its own rows (minus the sequence's history halo) behind its solve, the gather follows the step's last chunk
