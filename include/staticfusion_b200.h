@@ -233,7 +233,8 @@ int sf_last_launch_count(sf_ctx* ctx);
 int sf_last_lane_count(sf_ctx* ctx);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------- */
-#define SF_PROF_CLASSES 9 /* 0 init, 1 pyramid, 2 clustering, 3 warp, 4 linearise, 5 irls_pass1, 6 irls_pass2, 7 pose_update, 8 finish */
+#define SF_PROF_CLASSES 9 /* 0 init, 1 pyramid, 2 clustering, 3 warp, 4 linearise, 5 irls (the loop / fused kernels: whole IRLS loops; pass 1 with
+                             SF_IRLS_LOOP=0), 6 irls_pass2 (SF_IRLS_LOOP=0 only), 7 pose_update, 8 finish.  SF_NVTX=1 adds NVTX ranges per stage. */
 #define SF_PROF_LEVELS 8
 /* Record a CUDA-event pair around every kernel group of the following sf_launch calls (on the context's stream). */
 int sf_profile_enable(sf_ctx* ctx, int on);

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX: stage ranges for nsys / ncu --nvtx (SF_NVTX=1)
+
 #include "sf_kernels.cuh"
 
 using namespace sf;
@@ -110,10 +112,13 @@ static cudaEvent_t prof_event(sf_ctx* c) {
 // stream, so that the groups do not overlap): the events are recorded as EXTERNAL event nodes of the graph, i.e. the times
 // are those of the product's own execution mode, without the host-side launch gaps plain launches would add to every
 // small kernel.
+static const char* const kStageNames[SF_PROF_CLASSES] = {"sf:init", "sf:pyramid", "sf:clustering", "sf:warp", "sf:linearise", "sf:irls", "sf:irls_pass2",
+                                                         "sf:pose_update", "sf:finish"};
 struct ProfScope {
     sf_ctx* c;
     bool on;
     cudaEvent_t e1;
+    bool nvtx = false;
     static void record(sf_ctx* c, cudaEvent_t e) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(c->stream, &st);
@@ -121,13 +126,18 @@ struct ProfScope {
         else cudaEventRecord(e, c->stream);
     }
     ProfScope(sf_ctx* ctx, int cls, int level) : c(ctx), on(ctx->prof_on), e1(nullptr) {
+        static const bool want_nvtx = std::getenv("SF_NVTX") != nullptr;  // host-side ranges around the enqueue of every stage
+        if (want_nvtx && cls >= 0 && cls < SF_PROF_CLASSES) { nvtxRangePushA(kStageNames[cls]); nvtx = true; }
         if (!on) return;
         cudaEvent_t e0 = prof_event(c);
         e1 = prof_event(c);
         record(c, e0);
         c->prof.push_back({cls, level, e0, e1});
     }
-    ~ProfScope() { if (on) record(c, e1); }
+    ~ProfScope() {
+        if (on) record(c, e1);
+        if (nvtx) nvtxRangePop();
+    }
 };
 
 static void fill_dev_params(sf_ctx* c) {
