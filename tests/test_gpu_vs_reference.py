@@ -7,7 +7,8 @@
   what exact centre sums give (== the reference's except for a few boundary pixels on ~5 % of the pairs), iteration counts
   and b > 0.5 masks identical to the reference's, pose within 1e-5 wherever plain double sums manage that and never more than
   1e-6 farther from the reference than plain double sums;
-* BASELINE config 2 and the bench-shaped 512-pair / 3-lane batch against the oracle's EXACT policy, bit for bit.
+* BASELINE config 2 and the bench-shaped 512-pair batch (loop kernel, three lanes, per-launch IRLS passes) against the oracle's
+  EXACT policy, bit for bit.
 """
 import glob
 import os
