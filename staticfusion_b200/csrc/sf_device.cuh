@@ -26,15 +26,29 @@ constexpr uint8_t VLABEL_INVALID = 255; // pixel not in validPixels (FrontEnd.cp
 
 // Rows are stored as TILES: one 64-pixel tile = 14 planes x 64 floats followed by the 64 label bytes of those pixels
 // (255 = not in validPixels), 3648 contiguous bytes.  One tile = one cp.async.bulk (TMA bulk copy) into shared memory.
+// Every consumer of a tile is an order-independent integer sum over its pixels, so the ORDER of the pixels inside a tile is
+// free: it is chosen for the producer.  linearise_kernel's thread l of a 4-thread group holds the pixels 4l .. 4l+3 of a
+// 16-pixel group and stores them as two float2 per plane; pixel 4l + j sits at position 2l + (j & 1) + 8 (j >> 1) of the group, so
+// that four neighbouring threads fill one whole 32-byte sector with each store instruction instead of every other 8 bytes
+// (half-written sectors doubled the L1 -> L2 store traffic and bounded the kernel).  A 16-pixel group keeps its place in the
+// tile: the 32 positions a consumer's warp reads together are still 32 consecutive pixels of an image row (few label groups).
 constexpr int ROW_TILE = 64;
 constexpr int TILE_ROW_BYTES = ROW_TILE * NROWPL * 4;    // 3584
 constexpr int TILE_BYTES = TILE_ROW_BYTES + ROW_TILE;    // 3648 (multiple of 16)
 __host__ __device__ __forceinline__ size_t tiles_per_pair(size_t P0) { return (P0 + ROW_TILE - 1) / ROW_TILE; }
+__host__ __device__ __forceinline__ int tile_pos(int p) {                // position of pixel p inside its tile
+    const int r = p % ROW_TILE;
+#ifdef SF_TILE_LINEAR
+    return r;
+#else
+    return (r & ~15) + ((r >> 1) & 1) * 8 + (((r >> 2) & 3) << 1) + (r & 1);
+#endif
+}
 __host__ __device__ __forceinline__ size_t tile_row_off(int k, int p) {   // byte offset of row plane k of pixel p
-    return (size_t)(p / ROW_TILE) * TILE_BYTES + ((size_t)k * ROW_TILE + (size_t)(p % ROW_TILE)) * 4;
+    return (size_t)(p / ROW_TILE) * TILE_BYTES + ((size_t)k * ROW_TILE + (size_t)tile_pos(p)) * 4;
 }
 __host__ __device__ __forceinline__ size_t tile_label_off(int p) {        // byte offset of the label of pixel p
-    return (size_t)(p / ROW_TILE) * TILE_BYTES + TILE_ROW_BYTES + (size_t)(p % ROW_TILE);
+    return (size_t)(p / ROW_TILE) * TILE_BYTES + TILE_ROW_BYTES + (size_t)tile_pos(p);
 }
 
 // fixed-point scales of the order-independent sums (mirrored by the oracle's EXACT policy)

@@ -123,8 +123,8 @@ __device__ __forceinline__ PassRing pass_ring_setup(unsigned char* dyn_smem, int
 constexpr size_t PS_DYN_SMEM = PS_RING_BYTES + PS_WARPS * PS_STAGES * sizeof(unsigned long long);
 
 // ---- per-tile bodies shared by the multi-block passes and the fused per-pair kernel -------------------------------
-// A lane takes the pixels `lane` and `lane + 32` of the tile: conflict-free 4-byte shared loads, 32 consecutive pixels of
-// an image row per step (labels are spatially coherent, so pass 2's label groups are few).
+// A lane takes the tile positions `lane` and `lane + 32` (sf_device.cuh: 32 pixels out of 64 consecutive ones of
+// an image row per step; labels are spatially coherent, so pass 2's label groups are few): conflict-free 4-byte shared loads.
 // pass 1 on one tile: robust weights (:615-637) and the fixed-point normal equations (:640-641) of 2 pixels per lane
 __device__ __forceinline__ void pass1_tile(const unsigned char* tile, int lane, int it, float inv_max_c, float inv_max_d,
                                            float inv_c_Cauchy, const float* s_b, const float* var, const float* mc, const float* md,

@@ -60,15 +60,20 @@ __device__ __forceinline__ void build_rows(float d, float x, float y, float dcu,
 #ifndef SF_LIN_BPS
 #define SF_LIN_BPS 2  // resident blocks per SM: 128 registers, no spills (3 blocks = 85 registers spills ~400 B per thread and is 1.5x slower)
 #endif
-// STAGED: the four source planes of an item (its pixels plus one image row above and below: one contiguous range per plane)
-// arrive in shared memory by four bulk copies (cp.async.bulk, mbarrier completion) issued one item ahead into the other of two
-// stages, so DRAM latency is hidden by the copy engine instead of by resident warps (the kernel needs 128 registers = 16 warps
-// per SM); the unstaged form (read-only global loads) serves the levels whose two stages would not fit.
+// NS > 0 (staged): the four source planes of an item (its pixels plus one image row above and below: one contiguous range per
+// plane) arrive in shared memory by four bulk copies (cp.async.bulk, mbarrier completion) issued NS - 1 items ahead into a ring
+// of NS stages, so DRAM latency is hidden by the copy engine instead of by resident warps (the kernel needs 128 registers = 16
+// warps per SM).  A stage is handed back by its own "empty" mbarrier (one arrival per warp): only the issuing thread waits for
+// it, the warps of a block drift up to NS - 1 items apart and there is no block-wide barrier per item.  NS = 0 (read-only
+// global loads) serves the levels whose stages would not fit.
 constexpr int LIN_ITEM_PIXELS = SF_LIN_THREADS * 4;
+constexpr int LIN_WARPS = SF_LIN_THREADS / 32;
+constexpr int LIN_MAX_STAGES = 3;
 __host__ __device__ __forceinline__ int lin_span(int cols) { return LIN_ITEM_PIXELS + 2 * cols; }  // floats of one plane of one stage
-__host__ __device__ __forceinline__ size_t lin_dyn_smem(int cols) { return (size_t)2 * 4 * lin_span(cols) * sizeof(float) + 2 * sizeof(unsigned long long); }
-template <bool STAGED>
+__host__ __device__ __forceinline__ size_t lin_dyn_smem(int cols, int ns) { return (size_t)ns * 4 * lin_span(cols) * sizeof(float) + 2 * LIN_MAX_STAGES * sizeof(unsigned long long); }
+template <int NS>
 __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(Arena a, DevParams prm, LevelGeom g, int first, int blocks_per_pair) {
+    constexpr bool STAGED = NS > 0;
     // persistent grid over (active pair, 1024-pixel block) items.  A block takes a CONTIGUOUS range of items, i.e. mostly one
     // pair: the per-thread partial reductions stay in registers across items and are folded (warp -> block -> PairCtl) only
     // when the pair changes, not once per 4 pixels of every thread.  All sums are integer sums / maxima: any cut is exact.
@@ -89,8 +94,8 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     extern __shared__ __align__(128) unsigned char lin_smem[];
     const int span = lin_span(g.cols);
     float* const stage_mem = reinterpret_cast<float*>(lin_smem);
-    unsigned long long* const stage_bar = reinterpret_cast<unsigned long long*>(lin_smem + (size_t)2 * 4 * span * sizeof(float));
-    unsigned stage_phase = 0;  // parity bit per stage
+    unsigned long long* const full_bar = reinterpret_cast<unsigned long long*>(lin_smem + (size_t)NS * 4 * span * sizeof(float));
+    unsigned long long* const empty_bar = full_bar + LIN_MAX_STAGES;
     // first pixel / number of pixels an item needs of every plane, and the copies themselves (thread 0)
     auto item_range = [&](int it_, int& lo, int& n) {
         const int ip0 = (it_ - (it_ / blocks_per_pair) * blocks_per_pair) * LIN_ITEM_PIXELS;
@@ -106,16 +111,24 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
                                first ? a.pyr_d + (size_t)fp_ * a.pyr_stride + g.off : a.warp_d + (size_t)pr * a.P0,
                                first ? a.pyr_i + (size_t)fp_ * a.pyr_stride + g.off : a.warp_i + (size_t)pr * a.P0};
         const unsigned bytes = (unsigned)n * 4u;  // lo and n are multiples of 4 pixels: 16-byte aligned, 16-byte granular
-        mbar_arm(&stage_bar[st], 4u * bytes);
+        mbar_arm(&full_bar[st], 4u * bytes);
 #pragma unroll
-        for (int q = 0; q < 4; q++) bulk_load(stage_mem + ((size_t)st * 4 + q) * span, src[q] + lo, bytes, &stage_bar[st]);
+        for (int q = 0; q < 4; q++) bulk_load(stage_mem + ((size_t)st * 4 + q) * span, src[q] + lo, bytes, &full_bar[st]);
     };
     if (STAGED) {
-        if (tid < 2) mbar_init(&stage_bar[tid], 1);
+        if (tid < NS) { mbar_init(&full_bar[tid], 1); mbar_init(&empty_bar[tid], LIN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
-        if (tid == 0 && item0 < item1) issue_item(item0, 0);
+        if (tid == 0)
+            for (int q = 0; q < NS - 1; q++)
+                if (item0 + q < item1) issue_item(item0 + q, q);
     }
+    // ring state.  Consumers: stage / parity of the current item.  Issuing thread: the stage the item NS - 1 ahead goes into (the one
+    // read at the previous item) and the parity of that stage's last hand-back
+    int st = 0;
+    unsigned st_par = 0;
+    int iss_st = NS - 1;
+    unsigned iss_par = 1;
 
     // per-thread partial reductions of the current pair
     float t_maxc = 0.f, t_maxd = 0.f;
@@ -127,7 +140,20 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     int run_lab = -1, run_size = 0, run_nonnull = 0;
     long long run_prior = 0;
     int cur_pair = -1, items_since_fold = 0;
-    int cur_slot = -1, slot_pair = -1;  // the pair of the current slot stays in a register: one dependent global load per pair, not per item
+    // (slot, rem) = the item's pair slot and 1024-pixel block in it; the pair of the slot stays in a register (one dependent
+    // global load per pair, not per item) and the labels of an item are loaded one item ahead (their DRAM latency was the
+    // kernel's top stall: nothing else of an item comes from global memory)
+    int slot = item0 / blocks_per_pair, rem = item0 - slot * blocks_per_pair;
+    int pair_next = item0 < item1 ? a.active_list[slot] : 0;
+    // the prefetched labels stay ONE packed 32-bit register until the item that uses them: unpacked where they are loaded (as a
+    // uchar4 is), the byte extraction waits for the load at once
+    const unsigned none4 = 0x01010101u * LABEL_NONE;
+    auto load_labels = [&](int pr, int rem_) -> unsigned {
+        const int ch = rem_ * SF_LIN_THREADS + tid;
+        if (ch < (g.P >> 2)) return __ldg(reinterpret_cast<const unsigned*>(a.labels + (size_t)pr * a.pyr_stride + g.off + ((size_t)ch << 2)));
+        return none4;
+    };
+    unsigned l4n = item0 < item1 ? load_labels(pair_next, rem) : none4;
 
     // fold the block's partial reductions into the pair's cells (block-collective) and reset them
     auto flush = [&](int pair) {
@@ -186,14 +212,12 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
     };
 
   for (int item = item0; item < item1; item++) {
-    const int slot = item / blocks_per_pair;
-    if (slot != cur_slot) { cur_slot = slot; slot_pair = a.active_list[slot]; }
-    const int pair = slot_pair;
-    // this thread's four labels: issued before the wait for the staged planes, so that their latency hides behind it
-    const int chunk = (item - slot * blocks_per_pair) * SF_LIN_THREADS + tid;
+    const int pair = pair_next;
+    const int chunk = rem * SF_LIN_THREADS + tid;
     const bool inb = chunk < (g.P >> 2);
-    uchar4 l4 = make_uchar4(LABEL_NONE, LABEL_NONE, LABEL_NONE, LABEL_NONE);
-    if (inb) l4 = __ldg(reinterpret_cast<const uchar4*>(a.labels + (size_t)pair * a.pyr_stride + g.off + ((size_t)chunk << 2)));
+    const unsigned l4 = l4n;
+    if (++rem == blocks_per_pair) { rem = 0; slot++; if (item + 1 < item1) pair_next = a.active_list[slot]; }
+    if (item + 1 < item1) l4n = load_labels(pair_next, rem);  // consumed at the next item
     if (pair != cur_pair || items_since_fold == 128) {  // block-uniform
         if (cur_pair >= 0) flush(cur_pair);
         cur_pair = pair;
@@ -204,17 +228,19 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
         __syncthreads();
     }
 
-    const int st = (item - item0) & 1;
     int st_lo = 0;
     if (STAGED) {
-        if (tid == 0 && item + 1 < item1) {  // the other stage was last read before the barrier that ended the previous item
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_item(item + 1, st ^ 1);
+        if (tid == 0) {
+            if (item + (NS - 1) < item1) {
+                if (item > item0) mbar_wait(&empty_bar[iss_st], iss_par);  // every warp is done with the previous item's stage
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_item(item + (NS - 1), iss_st);
+            }
+            if (++iss_st == NS) { iss_st = 0; iss_par ^= 1u; }
         }
         int n_unused;
         item_range(item, st_lo, n_unused);
-        mbar_wait(&stage_bar[st], (stage_phase >> st) & 1u);
-        stage_phase ^= 1u << st;
+        mbar_wait(&full_bar[st], st_par);
     }
     const float* const sp = stage_mem + (size_t)st * 4 * span - st_lo;  // plane q of this item: sp[q * span + pixel]
     items_since_fold++;
@@ -222,9 +248,11 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
         const int padded = (int)tiles_per_pair((size_t)g.P) * (ROW_TILE / 4);
         if (!inb && chunk < padded) {
             uint8_t* tb = a.tiles + (size_t)pair * tiles_per_pair(a.P0) * TILE_BYTES;
-            *reinterpret_cast<uchar4*>(tb + tile_label_off(chunk << 2)) = make_uchar4(VLABEL_INVALID, VLABEL_INVALID, VLABEL_INVALID, VLABEL_INVALID);
-            for (int k = 0; k < NROWPL; k++)  // the passes multiply invalid pixels by a zero weight: rows must be finite
-                *reinterpret_cast<float4*>(tb + tile_row_off(k, chunk << 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int h = 0; h < 4; h += 2) {  // pixels (0, 1) and (2, 3) of the chunk are neighbours inside the tile
+                *reinterpret_cast<uchar2*>(tb + tile_label_off((chunk << 2) + h)) = make_uchar2(VLABEL_INVALID, VLABEL_INVALID);
+                for (int k = 0; k < NROWPL; k++)  // the passes multiply invalid pixels by a zero weight: rows must be finite
+                    *reinterpret_cast<float2*>(tb + tile_row_off(k, (chunk << 2) + h)) = make_float2(0.f, 0.f);
+            }
         }
     }
     const int fc = a.cur_idx[pair], fp = a.pred_idx[pair];
@@ -295,7 +323,7 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
                 ID[j] = 0.5f * (di4[j] + dwi4[j]);
             }
         }
-        const int ll[4] = {l4.x, l4.y, l4.z, l4.w};
+        const int ll[4] = {(int)(l4 & 255u), (int)((l4 >> 8) & 255u), (int)((l4 >> 16) & 255u), (int)(l4 >> 24)};
         float ro[NROWPL][2];  // rows of a pixel pair, stored as float2 (8 B per lane: full sectors)
         unsigned char ovl[4];
         const float cv = float(v) - g.disp_v;
@@ -389,9 +417,14 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
                     *reinterpret_cast<float2*>(tiles + tile_row_off(k, p0 + (j - 1))) = make_float2(ro[k][0], ro[k][1]);
             }
         }
-        *reinterpret_cast<uchar4*>(tiles + tile_label_off(p0)) = make_uchar4(ovl[0], ovl[1], ovl[2], ovl[3]);
+        *reinterpret_cast<uchar2*>(tiles + tile_label_off(p0)) = make_uchar2(ovl[0], ovl[1]);
+        *reinterpret_cast<uchar2*>(tiles + tile_label_off(p0 + 2)) = make_uchar2(ovl[2], ovl[3]);
     }
-    if (STAGED) __syncthreads();  // every thread is done with this item's stage before the copy after next overwrites it
+    if (STAGED) {  // this warp is done with the item's stage: hand it back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (++st == NS) { st = 0; st_par ^= 1u; }
+    }
   }
     if (cur_pair >= 0) flush(cur_pair);
 }
@@ -462,18 +495,27 @@ constexpr size_t LIN_MAX_STAGED_SMEM_PER_SM = 200 * 1024;  // the resident block
 int launch_linearise(const Arena& a, const DevParams& p, const LevelGeom& g, int first, const LaunchCfg& c) {
     const int bpp = (int)cdiv(tiles_per_pair((size_t)g.P) * (ROW_TILE / 4), SF_LIN_THREADS);
     const size_t items = (size_t)bpp * c.n_pairs, cap = (size_t)a.num_sms * 2 * SF_LIN_BPS;  // resident blocks per SM, two rounds
-    const size_t dyn = lin_dyn_smem(g.cols);
-    static const bool no_stage = std::getenv("SF_LIN_UNSTAGED") != nullptr;  // A-B measurements
-    if (!no_stage && dyn * SF_LIN_BPS <= LIN_MAX_STAGED_SMEM_PER_SM)
-        linearise_kernel<true><<<(unsigned)(items < cap ? items : cap), SF_LIN_THREADS, dyn, c.stream>>>(a, p, g, first, bpp);
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    static const int max_stages = [] {  // A-B measurements: SF_LIN_UNSTAGED, SF_LIN_STAGES=2|3
+        if (std::getenv("SF_LIN_UNSTAGED")) return 0;
+        const char* e = std::getenv("SF_LIN_STAGES");
+        const int v = e ? std::atoi(e) : LIN_MAX_STAGES;
+        return v < 2 ? 2 : (v > LIN_MAX_STAGES ? LIN_MAX_STAGES : v);
+    }();
+    if (max_stages >= 3 && lin_dyn_smem(g.cols, 3) * SF_LIN_BPS <= LIN_MAX_STAGED_SMEM_PER_SM)
+        linearise_kernel<3><<<grid, SF_LIN_THREADS, lin_dyn_smem(g.cols, 3), c.stream>>>(a, p, g, first, bpp);
+    else if (max_stages >= 2 && lin_dyn_smem(g.cols, 2) * SF_LIN_BPS <= LIN_MAX_STAGED_SMEM_PER_SM)
+        linearise_kernel<2><<<grid, SF_LIN_THREADS, lin_dyn_smem(g.cols, 2), c.stream>>>(a, p, g, first, bpp);
     else
-        linearise_kernel<false><<<(unsigned)(items < cap ? items : cap), SF_LIN_THREADS, 0, c.stream>>>(a, p, g, first, bpp);
+        linearise_kernel<0><<<grid, SF_LIN_THREADS, 0, c.stream>>>(a, p, g, first, bpp);
     return 1;
 }
 
 void linearise_kernel_attrs() {  // attribute setup for the current device, outside stream capture (called by prepare_kernels in every sf_create)
-    cudaFuncSetAttribute(linearise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LIN_MAX_STAGED_SMEM_PER_SM / SF_LIN_BPS));
-    cudaFuncSetAttribute(linearise_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 88);  // room for the stages of all resident blocks
+    cudaFuncSetAttribute(linearise_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LIN_MAX_STAGED_SMEM_PER_SM / SF_LIN_BPS));
+    cudaFuncSetAttribute(linearise_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 88);  // room for the stages of all resident blocks
+    cudaFuncSetAttribute(linearise_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LIN_MAX_STAGED_SMEM_PER_SM / SF_LIN_BPS));
+    cudaFuncSetAttribute(linearise_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 88);
 }
 
 int launch_step_prep(const Arena& a, const DevParams& p, int level_i, int k, const LaunchCfg& c) {

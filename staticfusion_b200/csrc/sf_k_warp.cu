@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(256, SF_WARP_BPS) warp_kernel(Arena a, LevelGe
     const float* src_d = nullptr;
     const float* src_i = nullptr;
     float T[12];  // the pair's inverse pose stays in registers while the block walks through the pair's pixels
+    // depth and intensity of an item are loaded together and ONE ITEM AHEAD (while the block stays inside a pair): the two
+    // dependent DRAM round trips per item (depth, then intensity only where the depth is valid) were 42 % of the stall samples
+    float z_n = 0.f, i_n = 0.f;
+    bool have_n = false;
     for (ItemWalk it(a.gcount[0] * chunks_per_pair, chunks_per_pair); it.more(); it.next()) {
         if (it.slot != cur_slot) {
             cur_slot = it.slot;
@@ -101,13 +105,22 @@ __global__ void __launch_bounds__(256, SF_WARP_BPS) warp_kernel(Arena a, LevelGe
             src_d = a.pyr_d + fo; src_i = a.pyr_i + fo;
 #pragma unroll
             for (int q = 0; q < 12; q++) T[q] = a.ctl[pair].Tinv[q];
+            have_n = false;
         }
         const int p = it.rem * 256 + threadIdx.x;
-        if (p >= g.P) continue;
-        if ((threadIdx.x & 7) == 0 && p + 256 < g.P) { prefetch_l2(src_d + p + 256); prefetch_l2(src_i + p + 256); }  // the next item's sectors
-        const float z = __ldg(src_d + p);
-        if (z == 0.f) continue;
-        const float intensity_w = __ldg(src_i + p);
+        float z = z_n, intensity_w = i_n;
+        if (!have_n) {
+            z = 0.f; intensity_w = 0.f;
+            if (p < g.P) { z = __ldg(src_d + p); intensity_w = __ldg(src_i + p); }
+        }
+        have_n = (it.rem + 1 < chunks_per_pair) && (it.item + 1 < it.end);  // block-uniform: the next item is in the same pair
+        if (have_n) {
+            const int pn = p + 256;
+            z_n = 0.f; i_n = 0.f;
+            if (pn < g.P) { z_n = __ldg(src_d + pn); i_n = __ldg(src_i + pn); }
+            if ((threadIdx.x & 7) == 0 && pn + 256 < g.P) { prefetch_l2(src_d + pn + 256); prefetch_l2(src_i + pn + 256); }  // the sectors of the item after
+        }
+        if (p >= g.P || z == 0.f) continue;
         int i, j;
         split_rc(p, g, i, j);
         const float xr = (g.inv_f * (float(j) - g.disp_u)) * z;  // xxPredPyr, FrontEnd.cpp:386
