@@ -102,9 +102,17 @@ __global__ void __launch_bounds__(SF_LIN_THREADS, SF_LIN_BPS) linearise_kernel(A
         lo = max(0, ip0 - g.cols);
         n = min(g.P, ip0 + LIN_ITEM_PIXELS + g.cols) - lo;
     };
+    // the issuing thread keeps (slot, pair, current frame, predicted frame) of the last issued item in shared memory: the two
+    // dependent global loads behind them would otherwise hold warp 0 - and, one ring later, every warp - for ~2 us per item
+    __shared__ int s_iss[4];
+    if (tid == 0) s_iss[0] = -1;
     auto issue_item = [&](int it_, int st) {
-        const int pr = a.active_list[it_ / blocks_per_pair];
-        const int fc_ = a.cur_idx[pr], fp_ = a.pred_idx[pr];
+        const int slot_ = it_ / blocks_per_pair;
+        if (slot_ != s_iss[0]) {
+            const int pr_ = a.active_list[slot_];
+            s_iss[0] = slot_; s_iss[1] = pr_; s_iss[2] = a.cur_idx[pr_]; s_iss[3] = a.pred_idx[pr_];
+        }
+        const int pr = s_iss[1], fc_ = s_iss[2], fp_ = s_iss[3];
         int lo, n;
         item_range(it_, lo, n);
         const float* src[4] = {a.pyr_d + (size_t)fc_ * a.pyr_stride + g.off, a.pyr_i + (size_t)fc_ * a.pyr_stride + g.off,
